@@ -1,0 +1,276 @@
+// Bandwidth-bound kernels around the tensor-core pipeline: im2col, prefix tokens, LayerNorm,
+// classifier head, q8_0 dequantisation, bicubic pos-embed resampling.  All are sized for HBM
+// streaming (16-byte vector accesses, one warp per token row, grids that cover every SM).
+#pragma once
+#include "ptx.cuh"
+
+namespace dino {
+
+// ---------------------------------------------------------------------------------------------
+// im2col for the 14x14 / stride-14 patch embedding (reference ggml_conv_2d -> im2col_f16,
+// ggml.c:3995-4017, ops.cpp:5784-5855): A[b*np + y*gw + x][c*ps*ps + ky*ps + kx] = fp16(img[c][y*ps+ky][x*ps+kx]),
+// zero-padded from 588 to `kpad` columns so the GEMM's 64-wide K boxes need no tail handling.
+// Input either RGB planar [B,3,H,W] (layout 0, what the reference uploads, dinov2.cpp:914-933) or the
+// cv::Mat layout [B,H,W,3] BGR-interleaved (layout 1) so the host never has to transpose.
+// One thread produces one (patch, channel, ky) run of `ps` contiguous kx values.
+__global__ void im2col_patch14_kernel(const float *__restrict__ img, __half *__restrict__ A, int B, int H, int W, int ps,
+                                      int gh, int gw, int kpad, int layout) {
+    const int runs_per_patch = 3 * ps;
+    const long long total = static_cast<long long>(B) * gh * gw * (runs_per_patch + 1);   // +1: the zero pad run
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int run = static_cast<int>(idx % (runs_per_patch + 1));
+        const long long patch = idx / (runs_per_patch + 1);
+        __half *dst = A + patch * kpad;
+        if (run == runs_per_patch) {
+            for (int k = 3 * ps * ps; k < kpad; ++k) dst[k] = __float2half_rn(0.f);
+            continue;
+        }
+        const int c = run / ps, ky = run % ps;
+        const int x = static_cast<int>(patch % gw);
+        const int y = static_cast<int>((patch / gw) % gh);
+        const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
+        const int py = y * ps + ky, px = x * ps;
+        dst += c * ps * ps + ky * ps;
+        if (layout == 0) {
+            const float *src = img + ((static_cast<size_t>(b) * 3 + c) * H + py) * W + px;
+            for (int kx = 0; kx < ps; ++kx) dst[kx] = __float2half_rn(__ldg(src + kx));
+        } else {
+            const float *src = img + ((static_cast<size_t>(b) * H + py) * W + px) * 3 + (2 - c);   // BGR -> RGB
+            for (int kx = 0; kx < ps; ++kx) dst[kx] = __float2half_rn(__ldg(src + 3 * kx));
+        }
+    }
+}
+
+// cls + pos[0] and the register tokens (no pos-embed) at the head of every image's token block
+// (reference dinov2.cpp:669-685).  grid = B, block covers D.
+__global__ void prefix_tokens_kernel(float *__restrict__ X, const float *__restrict__ cls, const float *__restrict__ pos,
+                                     const float *__restrict__ reg, int ntok, int D, int R) {
+    float *xb = X + static_cast<size_t>(blockIdx.x) * ntok * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        xb[d] = cls[d] + pos[d];
+        for (int r = 0; r < R; ++r) xb[(1 + r) * D + d] = reg[r * D + d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the hidden dimension, one warp per token (reference ggml_norm, ops.cpp:3109-3158:
+// mean, then centred variance, y = (x-mean)/sqrt(var+eps); followed by *weight + bias, dinov2.cpp:694-700).
+// OUT_HALF: writes the fp16 A operand of the next GEMM (the reference rounds it to fp16 inside mul_mat).
+// D <= 32 * 4 * LN_MAX_V4.
+constexpr int LN_MAX_V4 = 12;   // D up to 1536
+
+template <bool OUT_HALF>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
+                 void *__restrict__ out, int rows, int D, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nv = D >> 2;   // float4 per row
+    const float4 *x4 = reinterpret_cast<const float4 *>(X + static_cast<size_t>(warp) * D);
+    float4 v[LN_MAX_V4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i] = x4[idx];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / static_cast<float>(D) + eps);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+            const float y0 = (v[i].x * rstd) * g.x + b.x, y1 = (v[i].y * rstd) * g.y + b.y;
+            const float y2 = (v[i].z * rstd) * g.z + b.z, y3 = (v[i].w * rstd) * g.w + b.w;
+            if constexpr (OUT_HALF) {
+                uint2 *o2 = reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(out) + static_cast<size_t>(warp) * D);
+                o2[idx] = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+            } else {
+                float4 *o4 = reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + static_cast<size_t>(warp) * D);
+                o4[idx] = make_float4(y0, y1, y2, y3);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classifier head (reference forward_head, dinov2.cpp:792-821).
+// pooled[b][d] = (sum over tokens 1..ntok-1 of Y[b][t][d]) * (1 / n_embd^2): the divisor is the constant
+// (img_size/patch)^2 and the sum includes register tokens (dinov2.cpp:770-776, 800-803); ggml_sum_rows
+// accumulates in double.  feat[b] = [cls ; pooled]  ([B, 2D] fp32).
+__global__ void pool_tokens_kernel(const float *__restrict__ Y, float *__restrict__ feat, int ntok, int D, float inv_div) {
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const float *y = Y + static_cast<size_t>(b) * ntok * D + d;
+    double acc = 0.0;
+    for (int t = 1; t < ntok; ++t) acc += static_cast<double>(y[static_cast<size_t>(t) * D]);
+    feat[static_cast<size_t>(b) * 2 * D + d] = y[0];
+    feat[static_cast<size_t>(b) * 2 * D + D + d] = static_cast<float>(acc) * inv_div;
+}
+
+// logits[b][c] = sum_k fp16(feat[b][k]) * W[c][k] + bias[c]  (fp16 x fp16 -> f32, one warp per (b, c))
+__global__ void classifier_kernel(const float *__restrict__ feat, const __half *__restrict__ Wc, const float *__restrict__ bias,
+                                  float *__restrict__ logits, int B, int K, int C) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= B * C) return;
+    const int b = gw / C, c = gw % C;
+    const float *f = feat + static_cast<size_t>(b) * K;
+    const __half *w = Wc + static_cast<size_t>(c) * K;
+    float acc = 0.f;
+    for (int k = lane * 2; k < K; k += 64) {
+        const float2 wv = __half22float2(*reinterpret_cast<const __half2 *>(w + k));
+        acc = fmaf(__half2float(__float2half_rn(f[k])), wv.x, acc);
+        acc = fmaf(__half2float(__float2half_rn(f[k + 1])), wv.y, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) logits[static_cast<size_t>(b) * C + c] = acc + bias[c];
+}
+
+// probs = softmax(logits) per image (reference ggml_soft_max, ops.cpp:4641-4737). grid = B, block = 256.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ logits, float *__restrict__ probs, int C) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const float *x = logits + static_cast<size_t>(blockIdx.x) * C;
+    float *y = probs + static_cast<size_t>(blockIdx.x) * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) mx = fmaxf(mx, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        bcast = m;
+    }
+    __syncthreads();
+    mx = bcast;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const float e = expf(x[i] - mx);
+        y[i] = e;
+        sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        bcast = 1.0f / s;
+    }
+    __syncthreads();
+    const float inv = bcast;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) y[i] *= inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Load-time weight preparation.
+// q8_0 -> fp16: blocks of {half d; int8 q[32]} along K (reference ggml-common.h:209-213,
+// dequantize_row_q8_0 in ggml-quants.c).  One thread per block; `row_map` (optional) permutes output rows
+// (used to interleave SwiGLU gate/up rows per N tile).
+__global__ void dequant_q8_0_kernel(const uint8_t *__restrict__ raw, __half *__restrict__ W, long long n_blocks,
+                                    int blocks_per_row, int ld_out, const int *__restrict__ row_map) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_blocks;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint8_t *blk = raw + i * 34;
+        const float d = __half2float(__ushort_as_half(static_cast<unsigned short>(blk[0] | (blk[1] << 8))));
+        const long long row = i / blocks_per_row;
+        const int kb = static_cast<int>(i % blocks_per_row);
+        const long long orow = row_map ? row_map[row] : row;
+        __half *dst = W + orow * ld_out + kb * 32;
+        for (int j = 0; j < 32; ++j) dst[j] = __float2half_rn(d * static_cast<float>(static_cast<int8_t>(blk[2 + j])));
+    }
+}
+
+// fp16 [rows, K] -> fp16 [rows, ld_out] with optional row permutation and zero K padding
+__global__ void copy_rows_f16_kernel(const __half *__restrict__ src, __half *__restrict__ dst, long long rows, int K, int ld_out,
+                                     const int *__restrict__ row_map) {
+    const long long total = rows * ld_out;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / ld_out;
+        const int k = static_cast<int>(i % ld_out);
+        const long long orow = row_map ? row_map[row] : row;
+        dst[orow * ld_out + k] = k < K ? src[row * K + k] : __float2half_rn(0.f);
+    }
+}
+
+__global__ void permute_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int n, const int *__restrict__ map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[map[i]] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Positional-embedding resampling on device (reference interpolate_pos_embed, dinov2.cpp:159-225:
+// per channel cv::resize(INTER_CUBIC) of the M x M grid to gh x gw; cls row copied).  OpenCV convention:
+// src = (dst + 0.5) * (M / g) - 0.5, Keys cubic a = -0.75, replicated border, horizontal pass then vertical.
+__device__ __forceinline__ void cubic_w(float x, float w[4]) {
+    const float A = -0.75f;
+    w[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+    w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    w[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+    w[3] = 1.f - w[0] - w[1] - w[2];
+}
+__global__ void pos_embed_bicubic_kernel(const float *__restrict__ pos, float *__restrict__ out, int M, int gh, int gw, int D) {
+    // grid.x = 1 + gh*gw output rows, threads over D
+    const int row = blockIdx.x;
+    if (row == 0) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = pos[d];
+        return;
+    }
+    const int oy = (row - 1) / gw, ox = (row - 1) % gw;
+    const float fy = static_cast<float>((oy + 0.5) * (static_cast<double>(M) / gh) - 0.5);
+    const float fx = static_cast<float>((ox + 0.5) * (static_cast<double>(M) / gw) - 0.5);
+    const int sy = static_cast<int>(floorf(fy)), sx = static_cast<int>(floorf(fx));
+    float wy[4], wx[4];
+    cubic_w(fy - sy, wy);
+    cubic_w(fx - sx, wx);
+    int iy[4], ix[4];
+    for (int k = 0; k < 4; ++k) {
+        iy[k] = min(max(sy - 1 + k, 0), M - 1);
+        ix[k] = min(max(sx - 1 + k, 0), M - 1);
+    }
+    const float *grid = pos + D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            const float *r = grid + static_cast<size_t>(iy[a]) * M * D + d;
+            float h = r[static_cast<size_t>(ix[0]) * D] * wx[0];
+            h += r[static_cast<size_t>(ix[1]) * D] * wx[1];
+            h += r[static_cast<size_t>(ix[2]) * D] * wx[2];
+            h += r[static_cast<size_t>(ix[3]) * D] * wx[3];
+            acc = a == 0 ? h * wy[0] : acc + h * wy[a];
+        }
+        out[static_cast<size_t>(row) * D + d] = acc;
+    }
+}
+
+}  // namespace dino

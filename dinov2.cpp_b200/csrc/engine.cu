@@ -1,0 +1,932 @@
+// dinov2_b200 engine: weight residency, activation arena, kernel orchestration and the extern "C" ABI
+// declared in include/dinov2_b200.h.  Replaces the reference's graph build + ggml backend execution
+// (reference dinov2.cpp:616-838 forward_features/forward_head, :900-999 dino_predict) with a fixed fused
+// pipeline of hand-written sm_100a kernels.  There is no CPU fallback: without an sm_100 device every
+// entry point fails with DINO_B200_ERR_NO_DEVICE.
+#include "../../include/dinov2_b200.h"
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "gguf_reader.hpp"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace dino {
+
+// ------------------------------------------------------------------------------------------------ errors
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct StatusError : std::runtime_error {
+    dino_b200_status st;
+    StatusError(dino_b200_status s, const std::string &m) : std::runtime_error(m), st(s) {}
+};
+
+#define DINO_CUDA(expr)                                                                                        \
+    do {                                                                                                       \
+        cudaError_t err__ = (expr);                                                                            \
+        if (err__ != cudaSuccess)                                                                              \
+            throw dino::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(err__) + " (" __FILE__ \
+                                  ":" + std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+static thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    });
+    if (!fn) throw CudaError("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return fn;
+}
+
+// fp16 row-major [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-B swizzle;
+// out-of-bounds elements read as zero.
+static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {ld * sizeof(__half)};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstride[0] & 15)) throw CudaError("TMA operand is not 16-byte aligned");
+    const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+static int g_num_sms = 0;
+
+template <int BN, int EPI> static void configure_gemm() {
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+}
+static void configure_kernels_once() {
+    static std::once_flag once;
+    static std::string err;
+    std::call_once(once, [] {
+        try {
+            int dev = 0;
+            DINO_CUDA(cudaGetDevice(&dev));
+            DINO_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+            configure_gemm<256, EPI_BIAS_F16>();
+            configure_gemm<128, EPI_BIAS_F16>();
+            configure_gemm<256, EPI_GELU_F16>();
+            configure_gemm<128, EPI_GELU_F16>();
+            configure_gemm<256, EPI_RESID_F32>();
+            configure_gemm<128, EPI_RESID_F32>();
+            configure_gemm<256, EPI_SWIGLU_F16>();
+            configure_gemm<256, EPI_PATCH_F32>();
+            configure_gemm<128, EPI_PATCH_F32>();
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        } catch (const std::exception &e) {
+            err = e.what();
+        }
+    });
+    if (!err.empty()) throw CudaError(err);
+}
+
+static int pick_bn(int epi, int N) {
+    if (epi == EPI_SWIGLU_F16) return 256;
+    return (N % 256 == 0) ? 256 : 128;
+}
+
+template <int BN, int EPI>
+static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t st) {
+    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+    const int grid = std::max(1, std::min(tiles, g_num_sms));
+    gemm_f16_tcgen05<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(tmA, tmB, p);
+    DINO_CUDA(cudaGetLastError());
+}
+
+static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
+    if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
+#define DINO_GEMM_CASE(bn, e) \
+    if (BN == bn && epi == e) return launch_gemm_t<bn, e>(tmA, tmB, p, st)
+    DINO_GEMM_CASE(256, EPI_BIAS_F16);
+    DINO_GEMM_CASE(128, EPI_BIAS_F16);
+    DINO_GEMM_CASE(256, EPI_GELU_F16);
+    DINO_GEMM_CASE(128, EPI_GELU_F16);
+    DINO_GEMM_CASE(256, EPI_RESID_F32);
+    DINO_GEMM_CASE(128, EPI_RESID_F32);
+    DINO_GEMM_CASE(256, EPI_SWIGLU_F16);
+    DINO_GEMM_CASE(256, EPI_PATCH_F32);
+    DINO_GEMM_CASE(128, EPI_PATCH_F32);
+#undef DINO_GEMM_CASE
+    throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
+}
+
+static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, cudaStream_t st) {
+    AttnParams ap;
+    ap.n_tok = n_tok;
+    ap.hidden = D;
+    ap.out = out;
+    ap.scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
+    const dim3 grid((n_tok + ATT_BQ - 1) / ATT_BQ, D / ATT_HD, B);
+    attention_fwd_tcgen05<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ap);
+    DINO_CUDA(cudaGetLastError());
+}
+
+static void launch_layernorm(const float *X, const float *g, const float *b, void *out, int rows, int D, float eps, bool half_out,
+                             cudaStream_t st) {
+    if (D % 4 || D > 128 * LN_MAX_V4) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "layernorm: hidden size not supported");
+    const int grid = (rows + 7) / 8;
+    if (half_out) layernorm_kernel<true><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);
+    else layernorm_kernel<false><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);
+    DINO_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Linear {
+    __half *w = nullptr;   // [N, ldw]
+    float *bias = nullptr; // [N]
+    int N = 0, K = 0, ldw = 0, BN = 0;
+    CUtensorMap tm;
+};
+
+struct Layer {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ls1, *ls2;
+    Linear qkv, proj, fc1, fc2;
+};
+
+struct ProfileEvent {
+    cudaEvent_t a, b;
+    int kind;   // 0 gemm, 1 attention, 2 other
+};
+
+}  // namespace dino
+
+using namespace dino;
+
+struct dino_b200_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    dino_b200_hparams hp{};
+    bool swiglu = false;
+    int mlp_in = 0, mlp_hidden = 0;
+    std::vector<std::string> labels;
+
+    std::vector<void *> allocs;
+    Linear patch;
+    float *cls = nullptr, *pos = nullptr, *reg = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+    __half *wc = nullptr;
+    float *bc = nullptr;
+    std::vector<Layer> layers;
+    std::map<std::pair<int, int>, float *> pos_cache;
+
+    // activation arena (grown on demand)
+    size_t cap_tok = 0, cap_patch = 0, cap_img = 0, cap_batch = 0;
+    float *d_img = nullptr, *X = nullptr, *Y = nullptr, *feat = nullptr, *logits = nullptr, *probs = nullptr;
+    __half *Ape = nullptr, *Xn = nullptr, *QKV = nullptr, *AO = nullptr, *H1 = nullptr;
+    // host-API output staging in device memory
+    float *o_cls = nullptr, *o_patch = nullptr;
+    size_t cap_o_patch = 0;
+
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfileEvent> prof;
+    std::vector<ProfileEvent> prof_pool;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    std::string err;
+
+    void *dmalloc(size_t bytes) {
+        void *p = nullptr;
+        DINO_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        allocs.push_back(p);
+        return p;
+    }
+};
+
+namespace dino {
+
+struct TensorTable {
+    std::map<std::string, const dino_b200_tensor *> by_name;
+    const dino_b200_tensor &at(const std::string &n) const {
+        auto it = by_name.find(n);
+        if (it == by_name.end()) throw StatusError(DINO_B200_ERR_FORMAT, "checkpoint is missing tensor '" + n + "'");
+        return *it->second;
+    }
+    bool has(const std::string &n) const { return by_name.count(n) != 0; }
+};
+
+static int64_t numel(const dino_b200_tensor &t) {
+    int64_t n = 1;
+    for (int d = 0; d < t.n_dims; ++d) n *= t.ne[d];
+    return n;
+}
+
+static float *upload_f32(dino_b200_engine *e, const dino_b200_tensor &t, int64_t expect, const std::vector<int> *perm = nullptr) {
+    if (t.type != DINO_B200_TYPE_F32) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + t.name + "' must be F32");
+    if (numel(t) != expect)
+        throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + t.name + "' has " + std::to_string(numel(t)) +
+                                                    " elements, expected " + std::to_string(expect));
+    float *d = static_cast<float *>(e->dmalloc(expect * sizeof(float)));
+    if (perm) {
+        std::vector<float> tmp(expect);
+        const float *src = static_cast<const float *>(t.data);
+        for (int64_t i = 0; i < expect; ++i) tmp[(*perm)[i]] = src[i];
+        DINO_CUDA(cudaMemcpy(d, tmp.data(), expect * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        DINO_CUDA(cudaMemcpy(d, t.data, expect * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return d;
+}
+
+// Weight matrix [N, K] (ggml ne = [K, N], or [14,14,3,N] for the patch projection) -> device fp16 [N, ldw].
+static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor &w, const dino_b200_tensor &b, int N, int K,
+                          int epi, const std::vector<int> *perm, bool want_tmap = true) {
+    int64_t k_file = w.ne[0];
+    if (w.n_dims == 4) k_file = w.ne[0] * w.ne[1] * w.ne[2];
+    const int64_t n_file = numel(w) / k_file;
+    if (k_file != K || n_file != N)
+        throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' is [" + std::to_string(n_file) + ", " +
+                                                    std::to_string(k_file) + "], expected [" + std::to_string(N) + ", " +
+                                                    std::to_string(K) + "]");
+    L.N = N;
+    L.K = K;
+    L.ldw = (K + 63) / 64 * 64;
+    L.BN = pick_bn(epi, N);
+    L.w = static_cast<__half *>(e->dmalloc(static_cast<size_t>(N) * L.ldw * sizeof(__half)));
+    int *d_perm = nullptr;
+    if (perm) {
+        DINO_CUDA(cudaMalloc(&d_perm, N * sizeof(int)));
+        DINO_CUDA(cudaMemcpy(d_perm, perm->data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    const int grid = g_num_sms * 8;
+    if (w.type == DINO_B200_TYPE_F16) {
+        if (!perm && L.ldw == K) {
+            DINO_CUDA(cudaMemcpy(L.w, w.data, static_cast<size_t>(N) * K * sizeof(__half), cudaMemcpyHostToDevice));
+        } else {
+            __half *tmp = nullptr;
+            DINO_CUDA(cudaMalloc(&tmp, static_cast<size_t>(N) * K * sizeof(__half)));
+            DINO_CUDA(cudaMemcpy(tmp, w.data, static_cast<size_t>(N) * K * sizeof(__half), cudaMemcpyHostToDevice));
+            copy_rows_f16_kernel<<<grid, 256, 0, e->stream>>>(tmp, L.w, N, K, L.ldw, d_perm);
+            DINO_CUDA(cudaGetLastError());
+            DINO_CUDA(cudaStreamSynchronize(e->stream));
+            DINO_CUDA(cudaFree(tmp));
+        }
+    } else if (w.type == DINO_B200_TYPE_Q8_0) {
+        if (K % 32 || L.ldw != K) throw StatusError(DINO_B200_ERR_FORMAT, std::string("q8_0 tensor '") + w.name + "' has an unsupported row length");
+        uint8_t *raw = nullptr;
+        DINO_CUDA(cudaMalloc(&raw, w.nbytes));
+        DINO_CUDA(cudaMemcpy(raw, w.data, w.nbytes, cudaMemcpyHostToDevice));
+        dequant_q8_0_kernel<<<grid, 256, 0, e->stream>>>(raw, L.w, static_cast<long long>(N) * (K / 32), K / 32, L.ldw, d_perm);
+        DINO_CUDA(cudaGetLastError());
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        DINO_CUDA(cudaFree(raw));
+    } else if (w.type == DINO_B200_TYPE_F32) {
+        std::vector<__half> h(static_cast<size_t>(N) * L.ldw, __float2half(0.f));
+        const float *src = static_cast<const float *>(w.data);
+        for (int n = 0; n < N; ++n) {
+            const int on = perm ? (*perm)[n] : n;
+            for (int k = 0; k < K; ++k) h[static_cast<size_t>(on) * L.ldw + k] = __float2half_rn(src[static_cast<size_t>(n) * K + k]);
+        }
+        DINO_CUDA(cudaMemcpy(L.w, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    } else {
+        throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' has unsupported type " + std::to_string(w.type));
+    }
+    if (d_perm) DINO_CUDA(cudaFree(d_perm));
+    L.bias = upload_f32(e, b, N, perm);
+    // logical K columns = ldw: the pad columns are real zeros, so the K loop needs no tail case
+    if (want_tmap) L.tm = make_tmap_f16(L.w, L.ldw, N, L.ldw, L.BN);
+}
+
+static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) {
+    const dino_b200_hparams &hp = desc->hparams;
+    e->hp = hp;
+    if (e->hp.eps <= 0.f) e->hp.eps = 1e-6f;   // dino_hparams::eps default (dinov2.h:33)
+    const int D = hp.hidden_size, Lyr = hp.num_hidden_layers, H = hp.num_attention_heads, R = hp.num_register_tokens;
+    if (D <= 0 || Lyr <= 0 || H <= 0 || hp.patch_size == 0 || hp.img_size < hp.patch_size)
+        throw StatusError(DINO_B200_ERR_INVALID, "invalid hyper-parameters");
+    if (D % H || D / H != ATT_HD)
+        throw StatusError(DINO_B200_ERR_UNSUPPORTED, "attention kernel requires head_dim == 64 (every DINOv2 size has it)");
+    if (D % 64 || D > 128 * LN_MAX_V4) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "hidden size must be a multiple of 64 and <= 1536");
+    if (hp.patch_size != 14) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "patch size must be 14");
+
+    TensorTable tt;
+    for (int i = 0; i < desc->n_tensors; ++i) tt.by_name[desc->tensors[i].name] = &desc->tensors[i];
+
+    const int grid_m = hp.img_size / hp.patch_size;
+    e->cls = upload_f32(e, tt.at("embeddings.cls_token"), D);
+    e->pos = upload_f32(e, tt.at("embeddings.position_embeddings"), static_cast<int64_t>(1 + grid_m * grid_m) * D);
+    if (R > 0) e->reg = upload_f32(e, tt.at("embeddings.register_tokens"), static_cast<int64_t>(R) * D);
+    upload_linear(e, e->patch, tt.at("embeddings.patch_embeddings.projection.weight"),
+                  tt.at("embeddings.patch_embeddings.projection.bias"), D, 3 * hp.patch_size * hp.patch_size, EPI_PATCH_F32, nullptr);
+
+    e->swiglu = (Lyr == 40);   // the reference's own switch (dinov2.cpp:740)
+    e->layers.resize(Lyr);
+    for (int l = 0; l < Lyr; ++l) {
+        const std::string b = "encoder.layer." + std::to_string(l) + ".";
+        Layer &ly = e->layers[l];
+        ly.ln1_g = upload_f32(e, tt.at(b + "norm1.weight"), D);
+        ly.ln1_b = upload_f32(e, tt.at(b + "norm1.bias"), D);
+        ly.ln2_g = upload_f32(e, tt.at(b + "norm2.weight"), D);
+        ly.ln2_b = upload_f32(e, tt.at(b + "norm2.bias"), D);
+        ly.ls1 = upload_f32(e, tt.at(b + "layer_scale1.lambda1"), D);
+        ly.ls2 = upload_f32(e, tt.at(b + "layer_scale2.lambda1"), D);
+        upload_linear(e, ly.qkv, tt.at(b + "attention.attention.qkv.weight"), tt.at(b + "attention.attention.qkv.bias"), 3 * D, D,
+                      EPI_BIAS_F16, nullptr);
+        upload_linear(e, ly.proj, tt.at(b + "attention.output.dense.weight"), tt.at(b + "attention.output.dense.bias"), D, D,
+                      EPI_RESID_F32, nullptr);
+        if (e->swiglu) {
+            const dino_b200_tensor &win = tt.at(b + "mlp.weights_in.weight");
+            const int n_in = static_cast<int>(win.ne[1]);
+            if (n_in % 256) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "SwiGLU hidden size must be a multiple of 128");
+            const int hid = n_in / 2;
+            e->mlp_in = n_in;
+            e->mlp_hidden = hid;
+            // interleave per 256-row tile: rows [256t, 256t+128) = gate[128t..], rows [256t+128, 256t+256) = up[128t..]
+            std::vector<int> perm(n_in);
+            for (int j = 0; j < hid; ++j) {
+                perm[j] = (j / 128) * 256 + (j % 128);
+                perm[hid + j] = (j / 128) * 256 + 128 + (j % 128);
+            }
+            upload_linear(e, ly.fc1, win, tt.at(b + "mlp.weights_in.bias"), n_in, D, EPI_SWIGLU_F16, &perm);
+            upload_linear(e, ly.fc2, tt.at(b + "mlp.weights_out.weight"), tt.at(b + "mlp.weights_out.bias"), D, hid, EPI_RESID_F32, nullptr);
+        } else {
+            const dino_b200_tensor &w1 = tt.at(b + "mlp.fc1.weight");
+            const int n_in = static_cast<int>(w1.ne[1]);
+            e->mlp_in = n_in;
+            e->mlp_hidden = n_in;
+            upload_linear(e, ly.fc1, w1, tt.at(b + "mlp.fc1.bias"), n_in, D, EPI_GELU_F16, nullptr);
+            upload_linear(e, ly.fc2, tt.at(b + "mlp.fc2.weight"), tt.at(b + "mlp.fc2.bias"), D, n_in, EPI_RESID_F32, nullptr);
+        }
+    }
+    e->lnf_g = upload_f32(e, tt.at("layernorm.weight"), D);
+    e->lnf_b = upload_f32(e, tt.at("layernorm.bias"), D);
+    if (hp.num_classes > 0 && tt.has("classifier.weight")) {
+        Linear c;   // reuse the conversion path (q8_0 / f16 -> fp16 [C, 2D]); the head uses a GEMV kernel, not TMA tiles
+        upload_linear(e, c, tt.at("classifier.weight"), tt.at("classifier.bias"), hp.num_classes, 2 * D, EPI_BIAS_F16, nullptr, false);
+        e->wc = c.w;
+        e->bc = c.bias;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ arena
+static void free_arena(dino_b200_engine *e) {
+    void *ptrs[] = {e->d_img, e->X, e->Y, e->feat, e->logits, e->probs, e->Ape, e->Xn, e->QKV, e->AO, e->H1, e->o_cls, e->o_patch};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    e->d_img = e->X = e->Y = e->feat = e->logits = e->probs = e->o_cls = e->o_patch = nullptr;
+    e->Ape = e->Xn = e->QKV = e->AO = e->H1 = nullptr;
+    e->cap_tok = e->cap_patch = e->cap_img = e->cap_batch = e->cap_o_patch = 0;
+}
+
+template <typename T> static void arena_alloc(T *&p, size_t elems) {
+    DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(elems * sizeof(T), 16)));
+    DINO_CUDA(cudaMemset(p, 0, std::max<size_t>(elems * sizeof(T), 16)));
+}
+
+static void ensure_arena(dino_b200_engine *e, int B, int H, int W) {
+    const int ps = e->hp.patch_size, D = e->hp.hidden_size, R = e->hp.num_register_tokens;
+    const size_t np = static_cast<size_t>(H / ps) * (W / ps);
+    const size_t tok = static_cast<size_t>(B) * (1 + R + np), patch = static_cast<size_t>(B) * np;
+    const size_t img = static_cast<size_t>(B) * 3 * H * W;
+    if (tok <= e->cap_tok && patch <= e->cap_patch && img <= e->cap_img && static_cast<size_t>(B) <= e->cap_batch) return;
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    const size_t ntok = std::max(tok, e->cap_tok), npatch = std::max(patch, e->cap_patch), nimg = std::max(img, e->cap_img);
+    const size_t nb = std::max<size_t>(B, e->cap_batch);
+    free_arena(e);
+    // +128 rows of slack: attention / GEMM boxes may read (never write) past the last token row
+    const size_t rows = ntok + 128;
+    arena_alloc(e->d_img, nimg);
+    arena_alloc(e->Ape, (npatch + 128) * e->patch.ldw);
+    arena_alloc(e->X, rows * D);
+    arena_alloc(e->Y, rows * D);
+    arena_alloc(e->Xn, rows * D);
+    arena_alloc(e->QKV, rows * 3 * D);
+    arena_alloc(e->AO, rows * D);
+    arena_alloc(e->H1, rows * e->mlp_hidden);
+    arena_alloc(e->feat, nb * 2 * D);
+    arena_alloc(e->logits, nb * std::max<size_t>(e->hp.num_classes, 1));
+    arena_alloc(e->probs, nb * std::max<size_t>(e->hp.num_classes, 1));
+    arena_alloc(e->o_cls, nb * D);
+    e->cap_tok = ntok;
+    e->cap_patch = npatch;
+    e->cap_img = nimg;
+    e->cap_batch = nb;
+}
+
+static float *pos_for_grid(dino_b200_engine *e, int gh, int gw) {
+    const int M = e->hp.img_size / e->hp.patch_size, D = e->hp.hidden_size;
+    auto it = e->pos_cache.find({gh, gw});
+    if (it != e->pos_cache.end()) return it->second;
+    if (gh * gw == M * M) return e->pos;   // the reference's early return keys on the patch COUNT (dinov2.cpp:176-179)
+    float *buf = static_cast<float *>(e->dmalloc(static_cast<size_t>(1 + gh * gw) * D * sizeof(float)));
+    pos_embed_bicubic_kernel<<<1 + gh * gw, 128, 0, e->stream>>>(e->pos, buf, M, gh, gw, D);
+    DINO_CUDA(cudaGetLastError());
+    e->launches++;
+    e->pos_cache[{gh, gw}] = buf;
+    return buf;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+struct Prof {
+    dino_b200_engine *e;
+    cudaStream_t st;
+    void begin(int kind) {
+        if (!e->profiling) return;
+        ProfileEvent pe;
+        if (!e->prof_pool.empty()) {
+            pe = e->prof_pool.back();
+            e->prof_pool.pop_back();
+        } else {
+            DINO_CUDA(cudaEventCreate(&pe.a));
+            DINO_CUDA(cudaEventCreate(&pe.b));
+        }
+        pe.kind = kind;
+        DINO_CUDA(cudaEventRecord(pe.a, st));
+        e->prof.push_back(pe);
+    }
+    void end() {
+        if (!e->profiling) return;
+        DINO_CUDA(cudaEventRecord(e->prof.back().b, st));
+    }
+};
+
+static void forward_device(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
+                           float *patch, float *logits, float *probs, cudaStream_t st) {
+    const dino_b200_hparams &hp = e->hp;
+    const int ps = hp.patch_size, D = hp.hidden_size, R = hp.num_register_tokens;
+    if (!images || B <= 0 || H < ps || W < ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: bad batch or image size");
+    if (H % ps || W % ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: image size must be a multiple of the patch size");
+    if (layout != DINO_B200_LAYOUT_RGB_PLANAR && layout != DINO_B200_LAYOUT_BGR_HWC) throw StatusError(DINO_B200_ERR_INVALID, "forward: unknown image layout");
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    if ((logits || probs) && !classify) throw StatusError(DINO_B200_ERR_INVALID, "forward: logits/probs require DINO_B200_CLASSIFY");
+    if (classify && !e->wc) throw StatusError(DINO_B200_ERR_INVALID, "forward: checkpoint has no classifier head");
+
+    const int gh = H / ps, gw = W / ps, np = gh * gw, ntok = 1 + R + np;
+    const int M = B * ntok, Mp = B * np;
+    // every kernel launched below belongs to this engine; count them as we go
+    uint64_t &nl = e->launches;
+    Prof prof{e, st};
+    if (e->profiling) {
+        for (auto &pe : e->prof) e->prof_pool.push_back(pe);
+        e->prof.clear();
+        if (!e->ev_t0) {
+            DINO_CUDA(cudaEventCreate(&e->ev_t0));
+            DINO_CUDA(cudaEventCreate(&e->ev_t1));
+        }
+        DINO_CUDA(cudaEventRecord(e->ev_t0, st));
+    }
+
+    const float *pos = pos_for_grid(e, gh, gw);
+    if (st != e->stream) DINO_CUDA(cudaStreamSynchronize(e->stream));   // pos-embed resample ran on the engine stream
+
+    const CUtensorMap tm_ape = make_tmap_f16(e->Ape, e->patch.ldw, Mp, e->patch.ldw, GEMM_BM);
+    const CUtensorMap tm_xn = make_tmap_f16(e->Xn, D, M, D, GEMM_BM);
+    const CUtensorMap tm_ao = make_tmap_f16(e->AO, D, M, D, GEMM_BM);
+    const CUtensorMap tm_h1 = make_tmap_f16(e->H1, e->mlp_hidden, M, e->mlp_hidden, GEMM_BM);
+    const CUtensorMap tm_qkv = make_tmap_f16(e->QKV, 3 * D, M, 3 * D, ATT_BKV);
+
+    // 1. patch embedding: im2col -> GEMM (+bias +pos, scattered to token rows) ; cls/register rows
+    prof.begin(2);
+    {
+        const long long total = static_cast<long long>(Mp) * (3 * ps + 1);
+        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(g_num_sms) * 16));
+        im2col_patch14_kernel<<<grid, 256, 0, st>>>(images, e->Ape, B, H, W, ps, gh, gw, e->patch.ldw, layout);
+        DINO_CUDA(cudaGetLastError());
+        nl++;
+    }
+    prof.end();
+    {
+        GemmParams gp{};
+        gp.M = Mp; gp.N = D; gp.K = e->patch.ldw;
+        gp.bias = e->patch.bias; gp.out = e->X; gp.ldo = D;
+        gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = 1 + R;
+        prof.begin(0);
+        launch_gemm(EPI_PATCH_F32, e->patch.BN, tm_ape, e->patch.tm, gp, st);
+        prof.end();
+        nl++;
+    }
+    prof.begin(2);
+    prefix_tokens_kernel<<<B, 128, 0, st>>>(e->X, e->cls, pos, e->reg, ntok, D, R);
+    DINO_CUDA(cudaGetLastError());
+    nl++;
+    prof.end();
+
+    // 2. encoder blocks
+    for (const Layer &ly : e->layers) {
+        prof.begin(2);
+        launch_layernorm(e->X, ly.ln1_g, ly.ln1_b, e->Xn, M, D, hp.eps, true, st);
+        prof.end();
+        {
+            GemmParams gp{};
+            gp.M = M; gp.N = 3 * D; gp.K = D; gp.bias = ly.qkv.bias; gp.out = e->QKV; gp.ldo = 3 * D;
+            prof.begin(0);
+            launch_gemm(EPI_BIAS_F16, ly.qkv.BN, tm_xn, ly.qkv.tm, gp, st);
+            prof.end();
+        }
+        prof.begin(1);
+        launch_attention(tm_qkv, e->AO, B, ntok, D, st);
+        prof.end();
+        {
+            GemmParams gp{};
+            gp.M = M; gp.N = D; gp.K = D; gp.bias = ly.proj.bias; gp.lscale = ly.ls1; gp.out = e->X; gp.ldo = D;
+            prof.begin(0);
+            launch_gemm(EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, gp, st);
+            prof.end();
+        }
+        prof.begin(2);
+        launch_layernorm(e->X, ly.ln2_g, ly.ln2_b, e->Xn, M, D, hp.eps, true, st);
+        prof.end();
+        {
+            GemmParams gp{};
+            gp.M = M; gp.N = e->mlp_in; gp.K = D; gp.bias = ly.fc1.bias; gp.out = e->H1; gp.ldo = e->mlp_hidden;
+            prof.begin(0);
+            launch_gemm(e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16, ly.fc1.BN, tm_xn, ly.fc1.tm, gp, st);
+            prof.end();
+        }
+        {
+            GemmParams gp{};
+            gp.M = M; gp.N = D; gp.K = e->mlp_hidden; gp.bias = ly.fc2.bias; gp.lscale = ly.ls2; gp.out = e->X; gp.ldo = D;
+            prof.begin(0);
+            launch_gemm(EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, gp, st);
+            prof.end();
+        }
+        nl += 7;
+    }
+
+    // 3. final LayerNorm (all tokens: the head pools over registers too) + outputs
+    prof.begin(2);
+    launch_layernorm(e->X, e->lnf_g, e->lnf_b, e->Y, M, D, hp.eps, false, st);
+    nl++;
+    const size_t row_bytes = static_cast<size_t>(D) * sizeof(float);
+    if (cls) DINO_CUDA(cudaMemcpy2DAsync(cls, row_bytes, e->Y, ntok * row_bytes, row_bytes, B, cudaMemcpyDeviceToDevice, st));
+    if (patch)
+        DINO_CUDA(cudaMemcpy2DAsync(patch, np * row_bytes, e->Y + static_cast<size_t>(1 + R) * D, ntok * row_bytes, np * row_bytes, B,
+                                    cudaMemcpyDeviceToDevice, st));
+    if (classify) {
+        const int n_embd = hp.img_size / ps;
+        pool_tokens_kernel<<<dim3((D + 127) / 128, B), 128, 0, st>>>(e->Y, e->feat, ntok, D, 1.0f / static_cast<float>(n_embd * n_embd));
+        DINO_CUDA(cudaGetLastError());
+        const int C = hp.num_classes;
+        const long long warps = static_cast<long long>(B) * C;
+        classifier_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(e->feat, e->wc, e->bc, e->logits, B, 2 * D, C);
+        DINO_CUDA(cudaGetLastError());
+        nl += 2;
+        if (logits && logits != e->logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (probs) {
+            softmax_rows_kernel<<<B, 256, 0, st>>>(e->logits, probs, C);
+            DINO_CUDA(cudaGetLastError());
+            nl++;
+        }
+    }
+    prof.end();
+    if (e->profiling) DINO_CUDA(cudaEventRecord(e->ev_t1, st));
+}
+
+}  // namespace dino
+
+// ================================================================================================ C ABI
+#define DINO_API_BEGIN try {
+#define DINO_API_END(eng)                                                   \
+    }                                                                       \
+    catch (const dino::StatusError &ex) {                                   \
+        dino::g_last_error = ex.what();                                     \
+        if (eng) (eng)->err = ex.what();                                    \
+        return ex.st;                                                       \
+    }                                                                       \
+    catch (const dino::CudaError &ex) {                                     \
+        dino::g_last_error = ex.what();                                     \
+        if (eng) (eng)->err = ex.what();                                    \
+        return DINO_B200_ERR_CUDA;                                          \
+    }                                                                       \
+    catch (const std::exception &ex) {                                      \
+        dino::g_last_error = ex.what();                                     \
+        if (eng) (eng)->err = ex.what();                                    \
+        return DINO_B200_ERR_INVALID;                                       \
+    }
+
+static bool device_is_sm100(int dev) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    return major == 10;
+}
+
+extern "C" {
+
+int dino_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) ok += device_is_sm100(i) ? 1 : 0;
+    return ok;
+}
+
+static dino_b200_status require_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        dino::g_last_error = "no CUDA device visible: dinov2_b200 has no CPU fallback";
+        return DINO_B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        dino::g_last_error = "device index out of range";
+        return DINO_B200_ERR_INVALID;
+    }
+    if (!device_is_sm100(device)) {
+        dino::g_last_error = "device is not compute capability 10.x (kernels are built for sm_100a only)";
+        return DINO_B200_ERR_NO_DEVICE;
+    }
+    return DINO_B200_OK;
+}
+
+dino_b200_status dino_b200_create(const dino_b200_model_desc *desc, int device, dino_b200_engine **out) {
+    if (!desc || !out || (desc->n_tensors > 0 && !desc->tensors)) {
+        dino::g_last_error = "create: NULL argument";
+        return DINO_B200_ERR_INVALID;
+    }
+    *out = nullptr;
+    const dino_b200_status ds = require_device(device);
+    if (ds != DINO_B200_OK) return ds;
+    dino_b200_engine *e = nullptr;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(device));
+    configure_kernels_once();
+    e = new dino_b200_engine();
+    e->device = device;
+    DINO_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    try {
+        build_engine(e, desc);
+    } catch (...) {
+        dino_b200_destroy(e);
+        e = nullptr;
+        throw;
+    }
+    *out = e;
+    return DINO_B200_OK;
+    DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
+}
+
+dino_b200_status dino_b200_create_from_gguf(const char *path, int device, dino_b200_engine **out) {
+    if (!path || !out) {
+        dino::g_last_error = "create_from_gguf: NULL argument";
+        return DINO_B200_ERR_INVALID;
+    }
+    *out = nullptr;
+    dino::GGUFFile gg;
+    try {
+        dino::gguf_read(path, gg);
+    } catch (const std::exception &ex) {
+        dino::g_last_error = ex.what();
+        return std::string(ex.what()).rfind("cannot open", 0) == 0 || std::string(ex.what()).rfind("short read", 0) == 0
+                   ? DINO_B200_ERR_IO
+                   : DINO_B200_ERR_FORMAT;
+    }
+    auto need = [&](const char *k, uint32_t &dst) -> bool {
+        auto it = gg.kv_u.find(k);
+        if (it == gg.kv_u.end()) {
+            dino::g_last_error = std::string("gguf is missing key '") + k + "'";
+            return false;
+        }
+        dst = static_cast<uint32_t>(it->second);
+        return true;
+    };
+    dino_b200_model_desc desc{};
+    dino_b200_hparams &hp = desc.hparams;
+    if (!need("hidden_size", hp.hidden_size) || !need("num_hidden_layers", hp.num_hidden_layers) ||
+        !need("num_attention_heads", hp.num_attention_heads) || !need("patch_size", hp.patch_size) ||
+        !need("img_size", hp.img_size) || !need("ftype", hp.ftype) || !need("num_register_tokens", hp.num_register_tokens))
+        return DINO_B200_ERR_FORMAT;
+    hp.num_classes = gg.kv_u.count("num_classes") ? static_cast<uint32_t>(gg.kv_u["num_classes"]) : 0;
+    hp.ftype %= 1000;   // GGML_QNT_VERSION_FACTOR (dinov2.cpp:307)
+    hp.eps = 1e-6f;
+    std::vector<dino_b200_tensor> ts(gg.tensors.size());
+    for (size_t i = 0; i < ts.size(); ++i) {
+        const auto &t = gg.tensors[i];
+        ts[i].name = t.name.c_str();
+        ts[i].type = t.type;
+        ts[i].n_dims = t.n_dims;
+        for (int d = 0; d < 4; ++d) ts[i].ne[d] = t.ne[d];
+        ts[i].data = t.data;
+        ts[i].nbytes = t.nbytes;
+    }
+    desc.n_tensors = static_cast<int32_t>(ts.size());
+    desc.tensors = ts.data();
+    const dino_b200_status st = dino_b200_create(&desc, device, out);
+    if (st == DINO_B200_OK) {
+        (*out)->labels.resize(hp.num_classes);
+        for (uint32_t i = 0; i < hp.num_classes; ++i) {
+            auto it = gg.kv_s.find(std::to_string(i));
+            if (it != gg.kv_s.end()) (*out)->labels[i] = it->second;
+        }
+    }
+    return st;
+}
+
+void dino_b200_destroy(dino_b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    dino::free_arena(e);
+    for (void *p : e->allocs) cudaFree(p);
+    for (auto &pe : e->prof) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto &pe : e->prof_pool) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+dino_b200_status dino_b200_get_hparams(const dino_b200_engine *e, dino_b200_hparams *out) {
+    if (!e || !out) return DINO_B200_ERR_INVALID;
+    *out = e->hp;
+    return DINO_B200_OK;
+}
+
+const char *dino_b200_label(const dino_b200_engine *e, int class_id) {
+    if (!e || class_id < 0 || static_cast<size_t>(class_id) >= e->labels.size() || e->labels[class_id].empty()) return nullptr;
+    return e->labels[class_id].c_str();
+}
+
+dino_b200_status dino_b200_reserve(dino_b200_engine *e, int max_batch, int H, int W) {
+    if (!e || max_batch <= 0 || H <= 0 || W <= 0) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::ensure_arena(e, max_batch, H, W);
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_set_pos_embed(dino_b200_engine *e, int gh, int gw, const float *pos) {
+    if (!e || !pos || gh <= 0 || gw <= 0) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(e->device));
+    const size_t n = static_cast<size_t>(1 + gh * gw) * e->hp.hidden_size;
+    float *&slot = e->pos_cache[{gh, gw}];
+    if (!slot) slot = static_cast<float *>(e->dmalloc(n * sizeof(float)));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    DINO_CUDA(cudaMemcpy(slot, pos, n * sizeof(float), cudaMemcpyHostToDevice));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_get_pos_embed(dino_b200_engine *e, int H, int W, float *out) {
+    if (!e || !out || H <= 0 || W <= 0) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(e->device));
+    const int gh = H / e->hp.patch_size, gw = W / e->hp.patch_size;
+    if (gh <= 0 || gw <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "image smaller than one patch");
+    const float *p = dino::pos_for_grid(e, gh, gw);
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    DINO_CUDA(cudaMemcpy(out, p, static_cast<size_t>(1 + gh * gw) * e->hp.hidden_size * sizeof(float), cudaMemcpyDeviceToHost));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_forward_device(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags,
+                                          float *cls, float *patch, float *logits, float *probs, void *stream) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::ensure_arena(e, B > 0 ? B : 1, H, W);
+    dino::forward_device(e, images, layout, B, H, W, flags, cls, patch, logits, probs,
+                         stream ? static_cast<cudaStream_t>(stream) : e->stream);
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_forward(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
+                                   float *patch, float *logits, float *probs) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "forward: bad batch or image size");
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::ensure_arena(e, B, H, W);
+    const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
+    const size_t np = static_cast<size_t>(H / ps) * (W / ps);
+    if (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch) {
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->o_patch) DINO_CUDA(cudaFree(e->o_patch));
+        e->o_patch = nullptr;
+        e->cap_o_patch = 0;
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->o_patch), static_cast<size_t>(B) * np * D * sizeof(float)));
+        e->cap_o_patch = static_cast<size_t>(B) * np * D;
+    }
+    cudaStream_t st = e->stream;
+    DINO_CUDA(cudaMemcpyAsync(e->d_img, images, static_cast<size_t>(B) * 3 * H * W * sizeof(float), cudaMemcpyHostToDevice, st));
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    dino::forward_device(e, e->d_img, layout, B, H, W, flags, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
+                         (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
+    if (cls) DINO_CUDA(cudaMemcpyAsync(cls, e->o_cls, static_cast<size_t>(B) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (patch) DINO_CUDA(cudaMemcpyAsync(patch, e->o_patch, static_cast<size_t>(B) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs, e->probs, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DINO_CUDA(cudaStreamSynchronize(st));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_synchronize(dino_b200_engine *e) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    DINO_CUDA(cudaSetDevice(e->device));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+const char *dino_b200_last_error(const dino_b200_engine *e) { return e ? e->err.c_str() : dino::g_last_error.c_str(); }
+
+uint64_t dino_b200_kernel_launches(const dino_b200_engine *e) { return e ? e->launches : 0; }
+
+dino_b200_status dino_b200_set_profiling(dino_b200_engine *e, int on) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    e->profiling = on != 0;
+    return DINO_B200_OK;
+}
+
+dino_b200_status dino_b200_get_profile(dino_b200_engine *e, float *gemm_ms, float *attn_ms, float *other_ms, float *total_ms) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!e->ev_t1) throw dino::StatusError(DINO_B200_ERR_INVALID, "no profiled forward has run");
+    DINO_CUDA(cudaEventSynchronize(e->ev_t1));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (auto &pe : e->prof) {
+        float ms = 0.f;
+        DINO_CUDA(cudaEventElapsedTime(&ms, pe.a, pe.b));
+        acc[pe.kind] += ms;
+    }
+    float tot = 0.f;
+    DINO_CUDA(cudaEventElapsedTime(&tot, e->ev_t0, e->ev_t1));
+    if (gemm_ms) *gemm_ms = acc[0];
+    if (attn_ms) *attn_ms = acc[1];
+    if (other_ms) *other_ms = acc[2];
+    if (total_ms) *total_ms = tot;
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+// ------------------------------------------------------------------------------------------------ kernel hooks
+dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const void *W, int ldw, int M, int N, int K, const float *bias,
+                                       const float *lscale, void *out, int ldo, const float *pos, int np, int ntok, int tok_off,
+                                       void *stream) {
+    DINO_API_BEGIN
+    if (!A || !W || !out || !bias) throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_gemm: NULL argument");
+    int dev = 0;
+    DINO_CUDA(cudaGetDevice(&dev));
+    if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
+    configure_kernels_once();
+    const int BN = dino::pick_bn(epi, N);
+    const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN);
+    dino::GemmParams gp{};
+    gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = out; gp.ldo = ldo;
+    gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = tok_off;
+    dino::launch_gemm(epi, BN, tmA, tmB, gp, static_cast<cudaStream_t>(stream));
+    return DINO_B200_OK;
+    DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
+}
+
+dino_b200_status dino_b200_kernel_attention(const void *qkv, void *out, int B, int n_tok, int D, void *stream) {
+    DINO_API_BEGIN
+    if (!qkv || !out || B <= 0 || n_tok <= 0 || D <= 0 || D % ATT_HD) throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_attention: bad argument");
+    int dev = 0;
+    DINO_CUDA(cudaGetDevice(&dev));
+    if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
+    configure_kernels_once();
+    const CUtensorMap tm = dino::make_tmap_f16(qkv, 3 * D, static_cast<uint64_t>(B) * n_tok, 3 * D, ATT_BKV);
+    dino::launch_attention(tm, static_cast<__half *>(out), B, n_tok, D, static_cast<cudaStream_t>(stream));
+    return DINO_B200_OK;
+    DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
+}
+
+dino_b200_status dino_b200_kernel_layernorm(const float *X, const float *gamma, const float *beta, void *out, int rows, int D, float eps,
+                                            int out_half, void *stream) {
+    DINO_API_BEGIN
+    if (!X || !gamma || !beta || !out || rows <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_layernorm: bad argument");
+    dino::launch_layernorm(X, gamma, beta, out, rows, D, eps, out_half != 0, static_cast<cudaStream_t>(stream));
+    return DINO_B200_OK;
+    DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
+}
+
+}  // extern "C"

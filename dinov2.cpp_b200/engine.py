@@ -1,0 +1,222 @@
+"""ctypes binding of the C ABI in include/dinov2_b200.h (host side, Python).
+
+Mirrors the reference's operator surface for the hot path — load a gguf
+(`dino_model_load`, reference dinov2.cpp:239), run preprocessed images through
+the network (`dino_predict`, dinov2.cpp:900) — with batching added.  All
+compute happens in libdinov2_b200.so on an sm_100 GPU; there is NO CPU
+fallback: if the library or a B200 is missing these calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdinov2_b200.so")
+
+LAYOUT_RGB_PLANAR = 0
+LAYOUT_BGR_HWC = 1
+FLAG_CLASSIFY = 1
+
+EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_SWIGLU_F16, EPI_PATCH_F32 = range(5)
+
+STATUS = {0: "OK", 1: "ERR_INVALID", 2: "ERR_IO", 3: "ERR_FORMAT", 4: "ERR_CUDA", 5: "ERR_UNSUPPORTED", 6: "ERR_NO_DEVICE"}
+
+# every symbol include/dinov2_b200.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = [
+    "dino_b200_device_count", "dino_b200_create", "dino_b200_create_from_gguf", "dino_b200_destroy",
+    "dino_b200_get_hparams", "dino_b200_label", "dino_b200_reserve", "dino_b200_set_pos_embed",
+    "dino_b200_get_pos_embed", "dino_b200_forward", "dino_b200_forward_device", "dino_b200_synchronize",
+    "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
+    "dino_b200_kernel_gemm", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
+]
+
+
+class HParams(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_classes",
+                                           "num_register_tokens", "patch_size", "img_size", "ftype")] + [("eps", C.c_float)]
+
+
+class DinoB200Error(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"dinov2_b200: {STATUS.get(status, status)}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libdinov2_b200.so and declare prototypes. Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DinoB200Error(-1, f"{LIB_PATH} is missing — build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, fp, ip = C.c_void_p, C.c_void_p, C.c_int
+    L.dino_b200_device_count.restype = ip
+    L.dino_b200_create_from_gguf.argtypes = [C.c_char_p, ip, C.POINTER(vp)]
+    L.dino_b200_create.argtypes = [vp, ip, C.POINTER(vp)]
+    L.dino_b200_destroy.argtypes = [vp]
+    L.dino_b200_destroy.restype = None
+    L.dino_b200_get_hparams.argtypes = [vp, C.POINTER(HParams)]
+    L.dino_b200_label.argtypes = [vp, ip]
+    L.dino_b200_label.restype = C.c_char_p
+    L.dino_b200_reserve.argtypes = [vp, ip, ip, ip]
+    L.dino_b200_set_pos_embed.argtypes = [vp, ip, ip, fp]
+    L.dino_b200_get_pos_embed.argtypes = [vp, ip, ip, fp]
+    L.dino_b200_forward.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
+    L.dino_b200_forward_device.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp, vp]
+    L.dino_b200_synchronize.argtypes = [vp]
+    L.dino_b200_last_error.argtypes = [vp]
+    L.dino_b200_last_error.restype = C.c_char_p
+    L.dino_b200_kernel_launches.argtypes = [vp]
+    L.dino_b200_kernel_launches.restype = C.c_uint64
+    L.dino_b200_set_profiling.argtypes = [vp, ip]
+    pf = C.POINTER(C.c_float)
+    L.dino_b200_get_profile.argtypes = [vp, pf, pf, pf, pf]
+    L.dino_b200_kernel_gemm.argtypes = [ip, vp, ip, vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, ip, ip, ip, vp]
+    L.dino_b200_kernel_attention.argtypes = [vp, vp, ip, ip, ip, vp]
+    L.dino_b200_kernel_layernorm.argtypes = [vp, vp, vp, vp, ip, ip, C.c_float, ip, vp]
+    _lib = L
+    return L
+
+
+def _check(st: int, handle=None):
+    if st != 0:
+        L = load_library()
+        msg = L.dino_b200_last_error(handle)
+        raise DinoB200Error(st, (msg or b"").decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(load_library().dino_b200_device_count())
+
+
+def _host_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """One model resident on one GPU.  `forward` takes host arrays, `forward_device` raw device pointers."""
+
+    def __init__(self, gguf_path: str, device: int = 0):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.dino_b200_create_from_gguf(os.fsencode(gguf_path), device, C.byref(h)))
+        self._h = h
+        self.device = device
+        hp = HParams()
+        _check(L.dino_b200_get_hparams(self._h, C.byref(hp)), self._h)
+        self.hparams = {n: getattr(hp, n) for n, _ in HParams._fields_}
+        for k, v in self.hparams.items():
+            setattr(self, k, v)
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().dino_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- helpers -----------------------------------------------------------
+    def n_patches(self, H: int, W: int) -> int:
+        return (H // self.patch_size) * (W // self.patch_size)
+
+    def label(self, class_id: int) -> Optional[str]:
+        s = load_library().dino_b200_label(self._h, class_id)
+        return s.decode() if s else None
+
+    def reserve(self, max_batch: int, H: int, W: int):
+        _check(load_library().dino_b200_reserve(self._h, max_batch, H, W), self._h)
+
+    def set_pos_embed(self, gh: int, gw: int, pos: np.ndarray):
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        assert pos.shape == (1 + gh * gw, self.hidden_size)
+        _check(load_library().dino_b200_set_pos_embed(self._h, gh, gw, pos.ctypes.data), self._h)
+
+    def get_pos_embed(self, H: int, W: int) -> np.ndarray:
+        out = np.empty((1 + self.n_patches(H, W), self.hidden_size), np.float32)
+        _check(load_library().dino_b200_get_pos_embed(self._h, H, W, out.ctypes.data), self._h)
+        return out
+
+    def synchronize(self):
+        _check(load_library().dino_b200_synchronize(self._h), self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(load_library().dino_b200_kernel_launches(self._h))
+
+    def set_profiling(self, on: bool):
+        _check(load_library().dino_b200_set_profiling(self._h, int(on)), self._h)
+
+    def get_profile(self) -> Dict[str, float]:
+        v = [C.c_float() for _ in range(4)]
+        _check(load_library().dino_b200_get_profile(self._h, *[C.byref(x) for x in v]), self._h)
+        return dict(zip(("gemm_ms", "attn_ms", "other_ms", "total_ms"), [x.value for x in v]))
+
+    # -- the hot path ------------------------------------------------------
+    def forward(self, images: np.ndarray, classify: bool = False, layout: int = LAYOUT_BGR_HWC,
+                want_patch: bool = True, want_cls: bool = True, out: Optional[Dict[str, np.ndarray]] = None
+                ) -> Dict[str, np.ndarray]:
+        """images: float32 [B,H,W,3] (BGR_HWC, what dino_preprocess returns) or [B,3,H,W] (RGB_PLANAR).
+        Host in, host out; synchronous.  `out` may carry preallocated (e.g. pinned) result arrays."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        if images.ndim != 4:
+            raise ValueError("images must be 4-D")
+        if layout == LAYOUT_BGR_HWC:
+            B, H, W, ch = images.shape
+        else:
+            B, ch, H, W = images.shape
+        if ch != 3:
+            raise ValueError("images must have 3 channels")
+        D, NP, Cn = self.hidden_size, self.n_patches(H, W), self.num_classes
+        res = dict(out or {})
+        if want_cls and "cls" not in res:
+            res["cls"] = np.empty((B, D), np.float32)
+        if want_patch and "patch_tokens" not in res:
+            res["patch_tokens"] = np.empty((B, NP, D), np.float32)
+        if classify:
+            res.setdefault("logits", np.empty((B, Cn), np.float32))
+            res.setdefault("probs", np.empty((B, Cn), np.float32))
+        _check(load_library().dino_b200_forward(
+            self._h, images.ctypes.data, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
+            _host_ptr(res.get("cls")), _host_ptr(res.get("patch_tokens")),
+            _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))), self._h)
+        return res
+
+    def forward_device(self, images_ptr: int, layout: int, B: int, H: int, W: int, classify: bool = False,
+                       cls_ptr: int = 0, patch_ptr: int = 0, logits_ptr: int = 0, probs_ptr: int = 0, stream: int = 0):
+        """All pointers are device addresses (e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        _check(load_library().dino_b200_forward_device(
+            self._h, images_ptr, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
+            cls_ptr or None, patch_ptr or None, logits_ptr or None, probs_ptr or None, stream or None), self._h)
+
+
+# ---- kernel-level hooks (device pointers) ---------------------------------
+def kernel_gemm(epi: int, A: int, lda: int, W: int, ldw: int, M: int, N: int, K: int, bias: int, lscale: int, out: int,
+                ldo: int, pos: int = 0, np_: int = 0, ntok: int = 0, tok_off: int = 0, stream: int = 0):
+    _check(load_library().dino_b200_kernel_gemm(epi, A, lda, W, ldw, M, N, K, bias, lscale or None, out, ldo, pos or None,
+                                                np_, ntok, tok_off, stream or None))
+
+
+def kernel_attention(qkv: int, out: int, B: int, n_tok: int, D: int, stream: int = 0):
+    _check(load_library().dino_b200_kernel_attention(qkv, out, B, n_tok, D, stream or None))
+
+
+def kernel_layernorm(X: int, gamma: int, beta: int, out: int, rows: int, D: int, eps: float, out_half: bool, stream: int = 0):
+    _check(load_library().dino_b200_kernel_layernorm(X, gamma, beta, out, rows, D, eps, int(out_half), stream or None))

@@ -1,0 +1,11 @@
+"""Import alias: the package directory is named `dinov2.cpp_b200/` (a dot is
+not a legal Python identifier), so `import dinov2_b200` loads it from there."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "dinov2.cpp_b200")
+_spec = _u.spec_from_file_location("dinov2_b200", _os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["dinov2_b200"] = _mod
+_spec.loader.exec_module(_mod)

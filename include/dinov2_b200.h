@@ -1,0 +1,170 @@
+/*
+ * dinov2_b200.h — C ABI of the B200-native DINOv2 forward engine.
+ *
+ * This is the drop-in boundary for the reference's hot path: everything the reference does between
+ * "weights + a preprocessed image on the host" and "probabilities / patch tokens on the host", i.e.
+ * build_graph + ggml_backend_graph_compute inside dino_predict (reference dinov2.cpp:900-948) and all of
+ * ggml beneath it.  Plain C types only (pointers + sizes), status-code returns, caller-allocated outputs,
+ * no exceptions cross the boundary.  The C++ layer that keeps the reference's own API (dino_model_load /
+ * dino_predict ..., reference dinov2.h:94-118) on top of these calls is dinov2.cpp_b200/host/; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Threading: one engine per device, one in-flight forward per engine (the reference is single-caller too:
+ * dino_predict rebuilds its graph and shares one allocator, dinov2.cpp:907-910).
+ */
+#ifndef DINOV2_B200_H
+#define DINOV2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DINO_B200_API __attribute__((visibility("default")))
+#else
+#define DINO_B200_API
+#endif
+
+typedef struct dino_b200_engine dino_b200_engine;
+
+typedef enum {
+    DINO_B200_OK = 0,
+    DINO_B200_ERR_INVALID = 1,     /* bad argument (NULL, size not a patch multiple, ...) */
+    DINO_B200_ERR_IO = 2,          /* file could not be read */
+    DINO_B200_ERR_FORMAT = 3,      /* not a GGUF / missing tensor or key / unsupported tensor type */
+    DINO_B200_ERR_CUDA = 4,        /* CUDA runtime/driver failure; see dino_b200_last_error */
+    DINO_B200_ERR_UNSUPPORTED = 5, /* model shape outside what the kernels implement (head_dim != 64 ...) */
+    DINO_B200_ERR_NO_DEVICE = 6    /* no sm_100 device visible: there is deliberately NO CPU fallback */
+} dino_b200_status;
+
+/* Mirrors the numeric fields of the reference's dino_hparams (dinov2.h:25-45). */
+typedef struct {
+    uint32_t hidden_size;
+    uint32_t num_hidden_layers;
+    uint32_t num_attention_heads;
+    uint32_t num_classes;
+    uint32_t num_register_tokens;
+    uint32_t patch_size;
+    uint32_t img_size;
+    uint32_t ftype;
+    float eps;
+} dino_b200_hparams;
+
+/* ggml_type ids accepted for weights (reference ggml.h enum ggml_type). */
+enum { DINO_B200_TYPE_F32 = 0, DINO_B200_TYPE_F16 = 1, DINO_B200_TYPE_Q8_0 = 8 };
+
+/* One checkpoint tensor as the reference holds it in dino_model::tensors (dinov2.h:54): ggml `ne`
+ * (fastest dimension first) and a host pointer to the raw bytes. */
+typedef struct {
+    const char *name;
+    int32_t type;
+    int32_t n_dims;
+    int64_t ne[4];
+    const void *data;
+    uint64_t nbytes;
+} dino_b200_tensor;
+
+typedef struct {
+    dino_b200_hparams hparams;
+    int32_t n_tensors;
+    const dino_b200_tensor *tensors;
+} dino_b200_model_desc;
+
+/* image layouts of the `images` argument */
+enum {
+    DINO_B200_LAYOUT_RGB_PLANAR = 0, /* [B][3][H][W] float32 — what the reference uploads (dinov2.cpp:914-933) */
+    DINO_B200_LAYOUT_BGR_HWC = 1     /* [B][H][W][3] float32 — the cv::Mat dino_preprocess returns (dinov2.cpp:135-156) */
+};
+/* forward flags */
+enum { DINO_B200_CLASSIFY = 1 }; /* dino_params::classify (dinov2.h:63): run forward_head (dinov2.cpp:792-821) */
+
+/* Number of usable sm_100 devices (0 when none / no driver). */
+DINO_B200_API int dino_b200_device_count(void);
+
+/* Replaces the upload half of dino_model_load (dinov2.cpp:341-348: ggml_backend_alloc_ctx_tensors +
+ * ggml_backend_tensor_set): copies every tensor to `device`, converting to the engine's layouts
+ * (q8_0 -> fp16, patch-embed K padding, SwiGLU row interleave).  Host data may be freed afterwards. */
+DINO_B200_API dino_b200_status dino_b200_create(const dino_b200_model_desc *desc, int device, dino_b200_engine **out);
+
+/* Replaces dino_model_load end to end (dinov2.cpp:239-352: gguf_init_from_file + KV -> hparams + upload)
+ * with the engine's own GGUF reader. */
+DINO_B200_API dino_b200_status dino_b200_create_from_gguf(const char *path, int device, dino_b200_engine **out);
+
+/* Replaces ggml_backend_free / ggml_backend_buffer_free on the model (inference.cpp:72-73). */
+DINO_B200_API void dino_b200_destroy(dino_b200_engine *e);
+
+DINO_B200_API dino_b200_status dino_b200_get_hparams(const dino_b200_engine *e, dino_b200_hparams *out);
+
+/* id2label entry (dino_hparams::id2label, dinov2.cpp:300-304); NULL when the checkpoint has none. */
+DINO_B200_API const char *dino_b200_label(const dino_b200_engine *e, int class_id);
+
+/* Pre-sizes the activation arena for up to max_batch images of H x W (replaces ggml_gallocr_new +
+ * ggml_gallocr_alloc_graph, inference.cpp:63 / dinov2.cpp:910).  Optional: forward grows it on demand. */
+DINO_B200_API dino_b200_status dino_b200_reserve(dino_b200_engine *e, int max_batch, int H, int W);
+
+/* Optional override of the resampled positional embedding for a (gh x gw) patch grid:
+ * pos is [(1 + gh*gw)][D] float32 on the host, e.g. the output of the reference's host-side
+ * interpolate_pos_embed (dinov2.cpp:159-225, uploaded at :942).  Without it the engine resamples on the
+ * device with the same bicubic convention and caches the result per grid. */
+DINO_B200_API dino_b200_status dino_b200_set_pos_embed(dino_b200_engine *e, int gh, int gw, const float *pos);
+
+/* Copies the positional embedding the engine would use for an H x W input to the host
+ * ([(1 + (H/ps)*(W/ps))][D]); the device counterpart of interpolate_pos_embed. */
+DINO_B200_API dino_b200_status dino_b200_get_pos_embed(dino_b200_engine *e, int H, int W, float *out);
+
+/* The hot path: replaces build_graph + ggml_backend_graph_compute + output read-back of dino_predict
+ * (dinov2.cpp:907-991) for a batch of B already-preprocessed images in HOST memory.  Synchronous.
+ * Any output pointer may be NULL.
+ *   cls    [B][D]            final-LayerNorm class token                    (graph node "cls_token", :764-768)
+ *   patch  [B][NP][D]        final-LayerNorm patch tokens, registers stripped (node "patch_tokens", :770-789;
+ *                            what dino_predict copies into dino_output::patch_tokens, :980-991)
+ *   logits [B][num_classes]  classifier output before softmax (requires DINO_B200_CLASSIFY)
+ *   probs  [B][num_classes]  softmax(logits)                  (node "probs", :815-818)
+ * H and W must be multiples of patch_size (dino_preprocess guarantees it, :140-141). */
+DINO_B200_API dino_b200_status dino_b200_forward(dino_b200_engine *e, const float *images, int layout, int B, int H, int W,
+                                                 int flags, float *cls, float *patch, float *logits, float *probs);
+
+/* Same with every pointer in DEVICE memory; enqueues on `stream` (a cudaStream_t; NULL = the engine's own
+ * stream) and returns without synchronising. */
+DINO_B200_API dino_b200_status dino_b200_forward_device(dino_b200_engine *e, const float *images, int layout, int B, int H,
+                                                        int W, int flags, float *cls, float *patch, float *logits,
+                                                        float *probs, void *stream);
+
+/* Replaces ggml_backend_synchronize (inference.cpp:62,66). */
+DINO_B200_API dino_b200_status dino_b200_synchronize(dino_b200_engine *e);
+
+/* Last error text of the engine (or of the failed create call when e == NULL). Never NULL. */
+DINO_B200_API const char *dino_b200_last_error(const dino_b200_engine *e);
+
+/* Number of engine kernels launched since creation (bench.py reports the per-step delta as gpu_launches). */
+DINO_B200_API uint64_t dino_b200_kernel_launches(const dino_b200_engine *e);
+
+/* cudaEvent-timed duration (ms) of the GEMM kernels / attention kernels of the most recent
+ * dino_b200_forward* call when profiling is switched on (off by default; adds event records). */
+DINO_B200_API dino_b200_status dino_b200_set_profiling(dino_b200_engine *e, int on);
+DINO_B200_API dino_b200_status dino_b200_get_profile(dino_b200_engine *e, float *gemm_ms, float *attn_ms, float *other_ms,
+                                                     float *total_ms);
+
+/* ---- kernel-level entry points (device pointers), used by tests/ and bench.py to check and time each
+ * hand-written kernel in isolation against a plain fp32 restatement. stream may be NULL. ---- */
+enum { DINO_B200_EPI_BIAS_F16 = 0, DINO_B200_EPI_GELU_F16 = 1, DINO_B200_EPI_RESID_F32 = 2, DINO_B200_EPI_SWIGLU_F16 = 3,
+       DINO_B200_EPI_PATCH_F32 = 4 };
+/* C = A[M,K](fp16) x W[N,K]^T(fp16) with fused epilogue `epi` (see csrc/gemm.cuh). lda/ldw in elements.
+ * out: fp16 [M, ldo] for BIAS/GELU/SWIGLU (SWIGLU writes N/2 columns; W rows and bias pre-interleaved
+ * 128 gate | 128 up), fp32 [.., ldo] updated in place for RESID, written for PATCH. */
+DINO_B200_API dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const void *W, int ldw, int M, int N, int K,
+                                                     const float *bias, const float *lscale, void *out, int ldo,
+                                                     const float *pos, int np, int ntok, int tok_off, void *stream);
+/* out[B*N, D](fp16) = MHA(qkv[B*N, 3D](fp16)), head_dim 64 */
+DINO_B200_API dino_b200_status dino_b200_kernel_attention(const void *qkv, void *out, int B, int n_tok, int D, void *stream);
+/* LayerNorm rows of X[rows, D] -> fp16 (out_half != 0) or fp32 */
+DINO_B200_API dino_b200_status dino_b200_kernel_layernorm(const float *X, const float *gamma, const float *beta, void *out,
+                                                          int rows, int D, float eps, int out_half, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOV2_B200_H */
