@@ -234,6 +234,13 @@ struct TensorTable {
     bool has(const std::string &n) const { return by_name.count(n) != 0; }
 };
 
+// Every host->device upload is ordered on the engine's (non-blocking) stream: a plain cudaMemcpy from pageable
+// memory returns once the data is staged, possibly before the DMA lands, and the legacy default stream does not
+// synchronise with non-blocking streams — a conversion kernel launched right after could read stale bytes.
+static void h2d(dino_b200_engine *e, void *dst, const void *src, size_t bytes) {
+    DINO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
+}
+
 static int64_t numel(const dino_b200_tensor &t) {
     int64_t n = 1;
     for (int d = 0; d < t.n_dims; ++d) n *= t.ne[d];
@@ -250,9 +257,9 @@ static float *upload_f32(dino_b200_engine *e, const dino_b200_tensor &t, int64_t
         std::vector<float> tmp(expect);
         const float *src = static_cast<const float *>(t.data);
         for (int64_t i = 0; i < expect; ++i) tmp[(*perm)[i]] = src[i];
-        DINO_CUDA(cudaMemcpy(d, tmp.data(), expect * sizeof(float), cudaMemcpyHostToDevice));
+        h2d(e, d, tmp.data(), expect * sizeof(float));
     } else {
-        DINO_CUDA(cudaMemcpy(d, t.data, expect * sizeof(float), cudaMemcpyHostToDevice));
+        h2d(e, d, t.data, expect * sizeof(float));
     }
     return d;
 }
@@ -275,16 +282,16 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
     int *d_perm = nullptr;
     if (perm) {
         DINO_CUDA(cudaMalloc(&d_perm, N * sizeof(int)));
-        DINO_CUDA(cudaMemcpy(d_perm, perm->data(), N * sizeof(int), cudaMemcpyHostToDevice));
+        h2d(e, d_perm, perm->data(), N * sizeof(int));
     }
     const int grid = g_num_sms * 8;
     if (w.type == DINO_B200_TYPE_F16) {
         if (!perm && L.ldw == K) {
-            DINO_CUDA(cudaMemcpy(L.w, w.data, static_cast<size_t>(N) * K * sizeof(__half), cudaMemcpyHostToDevice));
+            h2d(e, L.w, w.data, static_cast<size_t>(N) * K * sizeof(__half));
         } else {
             __half *tmp = nullptr;
             DINO_CUDA(cudaMalloc(&tmp, static_cast<size_t>(N) * K * sizeof(__half)));
-            DINO_CUDA(cudaMemcpy(tmp, w.data, static_cast<size_t>(N) * K * sizeof(__half), cudaMemcpyHostToDevice));
+            h2d(e, tmp, w.data, static_cast<size_t>(N) * K * sizeof(__half));
             copy_rows_f16_kernel<<<grid, 256, 0, e->stream>>>(tmp, L.w, N, K, L.ldw, d_perm);
             DINO_CUDA(cudaGetLastError());
             DINO_CUDA(cudaStreamSynchronize(e->stream));
@@ -294,7 +301,7 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
         if (K % 32 || L.ldw != K) throw StatusError(DINO_B200_ERR_FORMAT, std::string("q8_0 tensor '") + w.name + "' has an unsupported row length");
         uint8_t *raw = nullptr;
         DINO_CUDA(cudaMalloc(&raw, w.nbytes));
-        DINO_CUDA(cudaMemcpy(raw, w.data, w.nbytes, cudaMemcpyHostToDevice));
+        h2d(e, raw, w.data, w.nbytes);
         dequant_q8_0_kernel<<<grid, 256, 0, e->stream>>>(raw, L.w, static_cast<long long>(N) * (K / 32), K / 32, L.ldw, d_perm);
         DINO_CUDA(cudaGetLastError());
         DINO_CUDA(cudaStreamSynchronize(e->stream));
@@ -306,10 +313,12 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
             const int on = perm ? (*perm)[n] : n;
             for (int k = 0; k < K; ++k) h[static_cast<size_t>(on) * L.ldw + k] = __float2half_rn(src[static_cast<size_t>(n) * K + k]);
         }
-        DINO_CUDA(cudaMemcpy(L.w, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        h2d(e, L.w, h.data(), h.size() * sizeof(__half));
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
     } else {
         throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' has unsupported type " + std::to_string(w.type));
     }
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
     if (d_perm) DINO_CUDA(cudaFree(d_perm));
     L.bias = upload_f32(e, b, N, perm);
     // logical K columns = ldw: the pad columns are real zeros, so the K loop needs no tail case
@@ -385,6 +394,7 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
         e->wc = c.w;
         e->bc = c.bias;
     }
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
 }
 
 // ------------------------------------------------------------------------------------------------ arena
@@ -397,9 +407,9 @@ static void free_arena(dino_b200_engine *e) {
     e->cap_tok = e->cap_patch = e->cap_img = e->cap_batch = e->cap_o_patch = 0;
 }
 
-template <typename T> static void arena_alloc(T *&p, size_t elems) {
+template <typename T> static void arena_alloc(T *&p, size_t elems, cudaStream_t st) {
     DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(elems * sizeof(T), 16)));
-    DINO_CUDA(cudaMemset(p, 0, std::max<size_t>(elems * sizeof(T), 16)));
+    DINO_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(elems * sizeof(T), 16), st));
 }
 
 static void ensure_arena(dino_b200_engine *e, int B, int H, int W) {
@@ -414,18 +424,19 @@ static void ensure_arena(dino_b200_engine *e, int B, int H, int W) {
     free_arena(e);
     // +128 rows of slack: attention / GEMM boxes may read (never write) past the last token row
     const size_t rows = ntok + 128;
-    arena_alloc(e->d_img, nimg);
-    arena_alloc(e->Ape, (npatch + 128) * e->patch.ldw);
-    arena_alloc(e->X, rows * D);
-    arena_alloc(e->Y, rows * D);
-    arena_alloc(e->Xn, rows * D);
-    arena_alloc(e->QKV, rows * 3 * D);
-    arena_alloc(e->AO, rows * D);
-    arena_alloc(e->H1, rows * e->mlp_hidden);
-    arena_alloc(e->feat, nb * 2 * D);
-    arena_alloc(e->logits, nb * std::max<size_t>(e->hp.num_classes, 1));
-    arena_alloc(e->probs, nb * std::max<size_t>(e->hp.num_classes, 1));
-    arena_alloc(e->o_cls, nb * D);
+    arena_alloc(e->d_img, nimg, e->stream);
+    arena_alloc(e->Ape, (npatch + 128) * e->patch.ldw, e->stream);
+    arena_alloc(e->X, rows * D, e->stream);
+    arena_alloc(e->Y, rows * D, e->stream);
+    arena_alloc(e->Xn, rows * D, e->stream);
+    arena_alloc(e->QKV, rows * 3 * D, e->stream);
+    arena_alloc(e->AO, rows * D, e->stream);
+    arena_alloc(e->H1, rows * e->mlp_hidden, e->stream);
+    arena_alloc(e->feat, nb * 2 * D, e->stream);
+    arena_alloc(e->logits, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
+    arena_alloc(e->probs, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
+    arena_alloc(e->o_cls, nb * D, e->stream);
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
     e->cap_tok = ntok;
     e->cap_patch = npatch;
     e->cap_img = nimg;
@@ -784,8 +795,8 @@ dino_b200_status dino_b200_set_pos_embed(dino_b200_engine *e, int gh, int gw, co
     const size_t n = static_cast<size_t>(1 + gh * gw) * e->hp.hidden_size;
     float *&slot = e->pos_cache[{gh, gw}];
     if (!slot) slot = static_cast<float *>(e->dmalloc(n * sizeof(float)));
+    h2d(e, slot, pos, n * sizeof(float));
     DINO_CUDA(cudaStreamSynchronize(e->stream));
-    DINO_CUDA(cudaMemcpy(slot, pos, n * sizeof(float), cudaMemcpyHostToDevice));
     return DINO_B200_OK;
     DINO_API_END(e)
 }

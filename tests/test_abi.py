@@ -1,0 +1,57 @@
+"""C-ABI library: loads, exports every symbol include/dinov2_b200.h declares, and fails loudly (no CPU
+fallback) when there is no B200.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dinov2_b200 as d
+from dinov2_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dinov2_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dino_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(E.ABI_SYMBOLS), "engine.py's symbol list drifted from the header"
+    L = ctypes.CDLL(E.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), f"libdinov2_b200.so does not export {s}"
+
+
+def test_header_is_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "dinov2_b200.h"\nint main(void){dino_b200_hparams h; (void)h; return DINO_B200_OK;}\n')
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                        str(tmp_path / "t.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_no_cpu_fallback_without_gpu():
+    if d.device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(d.DinoB200Error) as ei:
+        d.Engine(os.path.join(ROOT, "tests", "golden", "tiny_f16.gguf"))
+    assert ei.value.status == 6          # DINO_B200_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_bad_arguments_are_rejected_not_crashed():
+    L = d.load_library()
+    assert L.dino_b200_create_from_gguf(None, 0, None) == 1
+    assert L.dino_b200_forward(None, None, 0, 1, 14, 14, 0, None, None, None, None) == 1
+    assert L.dino_b200_kernel_launches(None) == 0
+    assert L.dino_b200_last_error(None) is not None
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dinov2.cpp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "restate" not in txt and "oracle/" not in txt.replace("oracle/Makefile", "").replace("oracle/_ref", "") or f == "core.hpp", f

@@ -1,0 +1,90 @@
+"""GGUF container + synthetic-checkpoint writer (CPU)."""
+import os
+
+import numpy as np
+import pytest
+
+import dinov2_b200  # noqa: F401
+from dinov2_b200 import gguf_io as G
+from dinov2_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_roundtrip(workdir):
+    cfg = synth.CONFIGS["tiny"]
+    p = os.path.join(workdir, "rt.gguf")
+    synth.write_synth_gguf(p, cfg, seed=3)
+    g = G.read_gguf(p)
+    assert g.kv["general.architecture"] == "dinov2"
+    assert g.kv["hidden_size"] == 128 and g.kv["num_register_tokens"] == 2 and g.kv["ftype"] == 1
+    assert g.kv["0"] == "class_0000" and g.kv["9"] == "class_0009"
+    ts = synth.make_tensors(cfg, seed=3)
+    assert list(g.tensors) == [t.name for t in ts]
+    for t in ts:
+        assert g.tensors[t.name].ne == t.ne and g.tensors[t.name].ggml_type == t.ggml_type
+        assert np.array_equal(g.tensors[t.name].data, t.data)
+
+
+def test_manifest_matches_reference_converter():
+    """Names / ggml shapes / dtypes of SURVEY.md appendix B (dumped from a file the reference converter wrote)."""
+    cfg = synth.CONFIGS["vits14_reg4"]
+    ts = {t.name: t for t in synth.make_tensors(synth.ModelConfig("x", 384, 1, 6, num_register_tokens=4), seed=0)}
+    D = 384
+    assert ts["embeddings.cls_token"].ne == (D, 1, 1) and ts["embeddings.cls_token"].ggml_type == G.GGML_TYPE_F32
+    assert ts["embeddings.position_embeddings"].ne == (D, 1370, 1)
+    assert ts["embeddings.register_tokens"].ne == (D, 4, 1)
+    assert ts["embeddings.patch_embeddings.projection.weight"].ne == (14, 14, 3, D)
+    assert ts["embeddings.patch_embeddings.projection.weight"].ggml_type == G.GGML_TYPE_F16
+    assert ts["embeddings.patch_embeddings.projection.bias"].ne == (1, 1, D, 1)
+    assert ts["encoder.layer.0.attention.attention.qkv.weight"].ne == (D, 3 * D)
+    assert ts["encoder.layer.0.mlp.fc1.weight"].ne == (D, 4 * D) and ts["encoder.layer.0.mlp.fc2.weight"].ne == (4 * D, D)
+    assert ts["classifier.weight"].ne == (2 * D, 1000)
+    assert list(ts)[-2:] == ["encoder.layer.0.attention.attention.qkv.weight", "encoder.layer.0.attention.attention.qkv.bias"]
+    assert len(synth.make_tensors(cfg, 0)) == 177 and len(synth.make_tensors(synth.CONFIGS["vits14"], 0)) == 176
+    g = synth.CONFIGS["vitg14"]
+    assert (g.mlp_in, g.mlp_hidden) == (8192, 4096)
+
+
+def test_q8_0_against_reference_quantize_tool():
+    """tiny_q8_0.gguf was written by the reference's `quantize` binary from tiny_f16.gguf."""
+    f16 = G.read_gguf(os.path.join(GOLD, "tiny_f16.gguf"))
+    q8 = G.read_gguf(os.path.join(GOLD, "tiny_q8_0.gguf"))
+    assert q8.kv["ftype"] == 8
+    n_q = 0
+    for name, t in q8.tensors.items():
+        src = f16.tensors[name]
+        if t.ggml_type == G.GGML_TYPE_Q8_0:
+            n_q += 1
+            assert name.endswith("weight") and len(t.ne) == 2          # dinov2.cpp:227-236
+            w = G.to_numpy(src).astype(np.float32)
+            mine = G.quantize_q8_0(w).reshape(-1, 34)
+            theirs = t.data.reshape(-1, 34)
+            assert np.array_equal(mine[:, :2], theirs[:, :2])            # block scales: bit-exact
+            dq = np.abs(mine[:, 2:].view(np.int8).astype(int) - theirs[:, 2:].view(np.int8).astype(int))
+            # the reference binary is built with -ffast-math (x*id vs x/d): rare off-by-one at .5 ties
+            assert dq.max() <= 1 and (dq != 0).mean() < 1e-3
+            deq = G.dequantize_q8_0(t.data, t.ne)
+            assert np.abs(deq - w).max() <= np.abs(w).max() / 127 * 0.51 + 1e-7
+        else:
+            assert t.ggml_type == src.ggml_type and np.array_equal(t.data, src.data)
+    assert n_q == 2 * 4 + 1                                              # qkv, dense, fc1, fc2 per layer + classifier
+
+
+def test_lcg_image_matches_scalar_definition():
+    img = synth.lcg_image(5, 4, 5)
+    s = (12345 + 5) & 0xFFFFFFFF
+    want = []
+    for _ in range(4 * 5 * 3):
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+        want.append(np.float32(((s >> 8) & 0xFFFF)) / np.float32(65535.0) * np.float32(4.0) - np.float32(2.0))
+    assert np.array_equal(img.reshape(-1), np.array(want, dtype=np.float32))
+    assert img.min() >= -2 and img.max() <= 2
+
+
+def test_reader_rejects_garbage(workdir):
+    p = os.path.join(workdir, "bad.gguf")
+    with open(p, "wb") as f:
+        f.write(b"NOTGGUF" + b"\0" * 64)
+    with pytest.raises(ValueError):
+        G.read_gguf(p)

@@ -1,0 +1,152 @@
+"""Hand-written sm_100a kernels in isolation, through the C ABI's kernel hooks, against a plain PyTorch fp32
+restatement of the same op.  Tolerances: fp16 outputs carry one rounding (rel 2^-11 ~ 4.9e-4 -> NMSE ~ 4e-8);
+fp32 outputs only differ by accumulation order."""
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import dinov2_b200 as d  # noqa: E402
+from dinov2_b200 import engine as E  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def nmse_t(got, ref):
+    got, ref = got.double(), ref.double()
+    return float(((got - ref) ** 2).sum() / (ref ** 2).sum().clamp_min(1e-30))
+
+
+def _operands(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    return A, W, bias, A.float() @ W.float().t() + bias
+
+
+# (M, N, K): single tile, ragged M, N not a multiple of the tile, the real ViT-S / ViT-L shapes, K tail via padding
+SHAPES = [(128, 128, 64), (200, 128, 128), (300, 384, 384), (2740, 1152, 384), (4096, 1024, 1024), (2740, 3072, 1024),
+          (1000, 512, 640), (1, 256, 128)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_bias_f16(M, N, K):
+    A, W, bias, ref = _operands(M, N, K)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+    E.kernel_gemm(E.EPI_BIAS_F16, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 0, out.data_ptr(), N)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, ref) < 2e-7
+    assert (out.float() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:6])
+def test_gemm_gelu_matches_fp16_table_semantics(M, N, K):
+    """gelu(x) = fp16(0.5 v (1 + tanh(c v (1 + a v^2)))) with v = fp16(x)  (reference vec.h:428-457)."""
+    A, W, bias, ref = _operands(M, N, K, seed=1)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+    E.kernel_gemm(E.EPI_GELU_F16, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 0, out.data_ptr(), N)
+    torch.cuda.synchronize()
+    v = ref.half().float()
+    want = (0.5 * v * (1 + torch.tanh(0.7978845608028654 * v * (1 + 0.044715 * v * v)))).half()
+    # identical up to fp32 accumulation order flipping an fp16 rounding of v: a few one-ulp differences at most
+    ulp_off = (out.view(torch.int16).int() - want.view(torch.int16).int()).abs()
+    assert int(ulp_off.max()) <= 2
+    assert float((ulp_off > 0).float().mean()) < 0.02
+    assert nmse_t(out, want) < 1e-7
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:6])
+def test_gemm_residual_layerscale_f32(M, N, K):
+    A, W, bias, ref = _operands(M, N, K, seed=2)
+    ls = torch.rand(N, device="cuda") + 0.3
+    X = torch.randn(M, N, device="cuda")
+    want = X + ls * ref
+    E.kernel_gemm(E.EPI_RESID_F32, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), X.data_ptr(), N)
+    torch.cuda.synchronize()
+    assert nmse_t(X, want) < 1e-11
+    assert (X - want).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,np_,toff", [(200, 128, 128, 100, 3), (300, 384, 640, 25, 1), (2738, 1024, 640, 1369, 5)])
+def test_gemm_patch_embed_epilogue(M, N, K, np_, toff):
+    """+bias +pos[1+p] and scatter to token row b*ntok + toff + p  (reference dinov2.cpp:636-685)."""
+    A, W, bias, ref = _operands(M, N, K, seed=3)
+    nimg, ntok = M // np_, toff + np_
+    pos = torch.randn(1 + np_, N, device="cuda")
+    X = torch.full((nimg * ntok, N), -7.0, device="cuda")
+    E.kernel_gemm(E.EPI_PATCH_F32, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 0, X.data_ptr(), N, pos.data_ptr(), np_, ntok, toff)
+    torch.cuda.synchronize()
+    X = X.view(nimg, ntok, N)
+    assert (X[:, :toff] == -7.0).all()                      # prefix rows untouched
+    assert nmse_t(X[:, toff:], ref.view(nimg, np_, N) + pos[1:]) < 1e-11
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (300, 1024, 192), (2740, 8192, 1536)])
+def test_gemm_swiglu(M, N, K):
+    """silu(gate) * up with rows interleaved 128 gate | 128 up per tile  (reference dinov2.cpp:577-606)."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    hid = N // 2
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    Wg = (torch.randn(hid, K, device="cuda", generator=g) * 0.05).half()
+    Wu = (torch.randn(hid, K, device="cuda", generator=g) * 0.05).half()
+    bg = torch.randn(hid, device="cuda", generator=g) * 0.1
+    bu = torch.randn(hid, device="cuda", generator=g) * 0.1
+    j = torch.arange(hid, device="cuda")
+    gi = (j // 128) * 256 + (j % 128)
+    Wi = torch.empty(N, K, device="cuda", dtype=torch.half)
+    bi = torch.empty(N, device="cuda")
+    Wi[gi], Wi[gi + 128], bi[gi], bi[gi + 128] = Wg, Wu, bg, bu
+    out = torch.full((M, hid), float("nan"), device="cuda", dtype=torch.half)
+    E.kernel_gemm(E.EPI_SWIGLU_F16, A.data_ptr(), K, Wi.data_ptr(), K, M, N, K, bi.data_ptr(), 0, out.data_ptr(), hid)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.silu(A.float() @ Wg.float().t() + bg) * (A.float() @ Wu.float().t() + bu)
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, want) < 2e-7
+
+
+# (B, N, D): one partial tile, exact tile, two tiles, the 518^2 token counts (1370 / 1374), the realtime-app count
+@pytest.mark.parametrize("B,N,D", [(1, 28, 128), (2, 128, 64), (2, 200, 128), (2, 1370, 384), (3, 1374, 128), (1, 2171, 64)])
+def test_attention(B, N, D):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Hh = D // 64
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).half()
+    out = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.half)
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    q, k, v = [t.view(B, N, Hh, 64).permute(0, 2, 1, 3) for t in qkv.float().split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, ref) < 5e-7
+
+
+def test_attention_large_logits_do_not_overflow():
+    """Online softmax must survive |s| far outside fp16's exp range (real checkpoints have outlier activations)."""
+    B, N, D = 1, 300, 64
+    g = torch.Generator(device="cuda").manual_seed(6)
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g)
+    qkv[:, :2 * D] *= 6.0                                   # logits/8 reach +-100
+    qkv = qkv.half()
+    out = torch.empty(B * N, D, device="cuda", dtype=torch.half)
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().split(D, dim=1)
+    ref = torch.softmax(q @ k.t() / 8.0, dim=-1) @ v
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("rows,D", [(28, 128), (100, 192), (2740, 384), (1000, 768), (4096, 1024), (999, 1536)])
+def test_layernorm(rows, D):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5
+    gam = torch.randn(D, device="cuda", generator=g)
+    bet = torch.randn(D, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(X.double(), (D,), gam.double(), bet.double(), 1e-6)
+    o16 = torch.empty(rows, D, device="cuda", dtype=torch.half)
+    o32 = torch.empty(rows, D, device="cuda")
+    E.kernel_layernorm(X.data_ptr(), gam.data_ptr(), bet.data_ptr(), o16.data_ptr(), rows, D, 1e-6, True)
+    E.kernel_layernorm(X.data_ptr(), gam.data_ptr(), bet.data_ptr(), o32.data_ptr(), rows, D, 1e-6, False)
+    torch.cuda.synchronize()
+    assert nmse_t(o32, ref) < 1e-12
+    assert nmse_t(o16, ref) < 2e-7
