@@ -6,6 +6,8 @@
 #include "../../include/dinov2_b200.h"
 
 #include "attention.cuh"
+#include "attention2.cuh"
+#include "attention3.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -16,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -63,20 +66,29 @@ static PFN_tmapEncodeTiled get_encode_fn() {
     return fn;
 }
 
-// fp16 row-major [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-B swizzle;
-// out-of-bounds elements read as zero.
-static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+// Row-major [rows, cols] tensor with row stride ld (elements); box = box_cols x box_rows with box_cols * elem = 128 B,
+// 128-B swizzle; out-of-bounds elements read as zero / are clipped on store.
+static CUtensorMap make_tmap_2d(const void *ptr, bool f32, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
     CUtensorMap m;
+    const size_t es = f32 ? sizeof(float) : sizeof(__half);
     const cuuint64_t gdim[2] = {cols, rows};
-    const cuuint64_t gstride[1] = {ld * sizeof(__half)};
-    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint64_t gstride[1] = {ld * es};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), box_rows};
     const cuuint32_t estr[2] = {1, 1};
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstride[0] & 15)) throw CudaError("TMA operand is not 16-byte aligned");
-    const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = get_encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                       const_cast<void *>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
     return m;
+}
+static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    return make_tmap_2d(ptr, false, cols, rows, ld, box_rows);
+}
+// output map of a GEMM epilogue: 32-row x 128-B boxes (one per epilogue warp and step)
+static CUtensorMap make_tmap_out(int epi, const void *out, uint64_t cols, uint64_t rows, uint64_t ld) {
+    return make_tmap_2d(out, epi == EPI_RESID_F32, cols, rows, ld, 32);
 }
 
 // ------------------------------------------------------------------------------------------------ launches
@@ -103,6 +115,8 @@ static void configure_kernels_once() {
             configure_gemm<256, EPI_PATCH_F32>();
             configure_gemm<128, EPI_PATCH_F32>();
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -116,18 +130,20 @@ static int pick_bn(int epi, int N) {
 }
 
 template <int BN, int EPI>
-static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t st) {
+static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
     const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
     const int grid = std::max(1, std::min(tiles, g_num_sms));
-    gemm_f16_tcgen05<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(tmA, tmB, p);
+    gemm_f16_tcgen05<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(tmA, tmB, tmC, p);
     DINO_CUDA(cudaGetLastError());
 }
 
-static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t st) {
+// tmC: output map (make_tmap_out) for every epilogue except PATCH, which scatters rows and ignores it
+static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p,
+                        cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
     if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
 #define DINO_GEMM_CASE(bn, e) \
-    if (BN == bn && epi == e) return launch_gemm_t<bn, e>(tmA, tmB, p, st)
+    if (BN == bn && epi == e) return launch_gemm_t<bn, e>(tmA, tmB, tmC, p, st)
     DINO_GEMM_CASE(256, EPI_BIAS_F16);
     DINO_GEMM_CASE(128, EPI_BIAS_F16);
     DINO_GEMM_CASE(256, EPI_GELU_F16);
@@ -141,14 +157,58 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
+// DINO_B200_ATTN=1|2 selects an earlier generation of the attention kernel for A/B comparisons (default: 3).
+static int attention_variant() {
+    static int v = [] {
+        const char *e = getenv("DINO_B200_ATTN");
+        return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 3;
+    }();
+    return v;
+}
+
 static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, cudaStream_t st) {
-    AttnParams ap;
-    ap.n_tok = n_tok;
-    ap.hidden = D;
-    ap.out = out;
-    ap.scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
-    const dim3 grid((n_tok + ATT_BQ - 1) / ATT_BQ, D / ATT_HD, B);
-    attention_fwd_tcgen05<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ap);
+    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
+    if (attention_variant() == 1) {
+        AttnParams ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        const dim3 grid((n_tok + ATT_BQ - 1) / ATT_BQ, D / ATT_HD, B);
+        attention_fwd_tcgen05<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 2) {
+        Attn2Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
+        attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else {
+        Attn3Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        static const int pingpong = [] { const char *e = getenv("DINO_B200_ATTN_PINGPONG"); return (e && e[0] == '1') ? 1 : 0; }();
+        ap.pingpong = pingpong;
+        ap.trace = nullptr;
+#ifdef AT3_TRACE
+        {
+            static unsigned long long *tr = nullptr;
+            if (!tr) { cudaMalloc(&tr, 3 * 512 * 2 * 8); }
+            cudaMemsetAsync(tr, 0, 3 * 512 * 2 * 8, st);
+            ap.trace = tr;
+            if (const char *f = getenv("DINO_B200_TRACE_PTR")) { FILE *fp = fopen(f, "w"); if (fp) { fprintf(fp, "%llu\n", (unsigned long long) tr); fclose(fp); } }
+        }
+#endif
+        static const int grid_mult = [] { const char *e = getenv("DINO_B200_ATTN_GRID"); return e ? atoi(e) : 1; }();
+        const int grid = grid_mult <= 0 ? ap.num_items : std::max(1, std::min(ap.num_items, g_num_sms * grid_mult));
+        attention_fwd_v3<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(tmQKV, ap);
+    }
     DINO_CUDA(cudaGetLastError());
 }
 
@@ -514,6 +574,9 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
     const CUtensorMap tm_ao = make_tmap_f16(e->AO, D, M, D, GEMM_BM);
     const CUtensorMap tm_h1 = make_tmap_f16(e->H1, e->mlp_hidden, M, e->mlp_hidden, GEMM_BM);
     const CUtensorMap tm_qkv = make_tmap_f16(e->QKV, 3 * D, M, 3 * D, ATT_BKV);
+    const CUtensorMap tmo_qkv = make_tmap_out(EPI_BIAS_F16, e->QKV, 3 * D, M, 3 * D);
+    const CUtensorMap tmo_h1 = make_tmap_out(EPI_GELU_F16, e->H1, e->mlp_hidden, M, e->mlp_hidden);
+    const CUtensorMap tmo_x = make_tmap_out(EPI_RESID_F32, e->X, D, M, D);
 
     // 1. patch embedding: im2col -> GEMM (+bias +pos, scattered to token rows) ; cls/register rows
     prof.begin(2);
@@ -531,7 +594,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         gp.bias = e->patch.bias; gp.out = e->X; gp.ldo = D;
         gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = 1 + R;
         prof.begin(0);
-        launch_gemm(EPI_PATCH_F32, e->patch.BN, tm_ape, e->patch.tm, gp, st);
+        launch_gemm(EPI_PATCH_F32, e->patch.BN, tm_ape, e->patch.tm, tmo_x, gp, st);
         prof.end();
         nl++;
     }
@@ -550,7 +613,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = 3 * D; gp.K = D; gp.bias = ly.qkv.bias; gp.out = e->QKV; gp.ldo = 3 * D;
             prof.begin(0);
-            launch_gemm(EPI_BIAS_F16, ly.qkv.BN, tm_xn, ly.qkv.tm, gp, st);
+            launch_gemm(EPI_BIAS_F16, ly.qkv.BN, tm_xn, ly.qkv.tm, tmo_qkv, gp, st);
             prof.end();
         }
         prof.begin(1);
@@ -560,7 +623,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = D; gp.K = D; gp.bias = ly.proj.bias; gp.lscale = ly.ls1; gp.out = e->X; gp.ldo = D;
             prof.begin(0);
-            launch_gemm(EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, gp, st);
+            launch_gemm(EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, tmo_x, gp, st);
             prof.end();
         }
         prof.begin(2);
@@ -570,14 +633,14 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = e->mlp_in; gp.K = D; gp.bias = ly.fc1.bias; gp.out = e->H1; gp.ldo = e->mlp_hidden;
             prof.begin(0);
-            launch_gemm(e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16, ly.fc1.BN, tm_xn, ly.fc1.tm, gp, st);
+            launch_gemm(e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16, ly.fc1.BN, tm_xn, ly.fc1.tm, tmo_h1, gp, st);
             prof.end();
         }
         {
             GemmParams gp{};
             gp.M = M; gp.N = D; gp.K = e->mlp_hidden; gp.bias = ly.fc2.bias; gp.lscale = ly.ls2; gp.out = e->X; gp.ldo = D;
             prof.begin(0);
-            launch_gemm(EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, gp, st);
+            launch_gemm(EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, tmo_x, gp, st);
             prof.end();
         }
         nl += 7;
@@ -913,7 +976,10 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     dino::GemmParams gp{};
     gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = out; gp.ldo = ldo;
     gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = tok_off;
-    dino::launch_gemm(epi, BN, tmA, tmB, gp, static_cast<cudaStream_t>(stream));
+    const int out_cols = epi == DINO_B200_EPI_SWIGLU_F16 ? N / 2 : N;
+    const uint64_t out_rows = epi == DINO_B200_EPI_PATCH_F32 ? static_cast<uint64_t>(M / (np > 0 ? np : 1)) * ntok : static_cast<uint64_t>(M);
+    const CUtensorMap tmC = dino::make_tmap_out(epi, out, out_cols, out_rows, ldo);
+    dino::launch_gemm(epi, BN, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }

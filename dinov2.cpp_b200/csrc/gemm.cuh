@@ -3,17 +3,22 @@
 //
 //     C[M, N] = A[M, K] (fp16, K contiguous)  x  W[N, K]^T (fp16, K contiguous)        + fused epilogue
 //
-// Roles (384 threads, 1 CTA / SM, grid = min(tiles, #SM), static round-robin tile schedule):
-//   warp 0      TMA producer: 128x64 A box + BNx64 W box per stage, 128B-swizzled, mbarrier tx-count
-//   warp 1      MMA issuer: one lane issues 4 x tcgen05.mma (128 x BN x 16) per stage into TMEM
-//   warp 2      TMEM allocator (512 columns = 2 accumulator stages x BN fp32 columns)
-//   warps 4-11  epilogue: tcgen05.ld 32x32b.x32 -> registers -> fused op -> global
+// Roles (384 threads, 1 CTA / SM, grid = min(tiles, #SM), static round-robin tile schedule).  The single-thread
+// TMA and MMA roles sit in the HIGHEST warp ids: the sub-partition arbiter prefers the highest eligible warp id, and
+// an MMA issuer that has to queue behind busy epilogue warps leaves the tensor pipe idle (measured with a cycle trace:
+// ~100 cycles per tcgen05.mma issue when the issuer was warp 1).
+//   warp 11     MMA issuer: one lane issues 4 x tcgen05.mma (128 x BN x 16) per stage into TMEM
+//   warp 10     TMA producer: 128x64 A box + BNx64 W box per stage, 128B-swizzled, mbarrier tx-count
+//   warp 8      TMEM allocator (512 columns = 2 accumulator stages x BN fp32 columns)
+//   warps 0-7   epilogue: tcgen05.ld 32x32b.x32 -> registers -> fused op -> 128B-swizzled smem staging (4 KB per warp)
+//               -> TMA store (fp16 outputs) or TMA reduce-add (fp32 residual stream): every global access is a full
+//               coalesced 128-B row segment, and the residual read-modify-write happens in the memory system
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), tile loop.
 //
 // Fused epilogues (each cites the reference graph ops it absorbs):
 //   EPI_BIAS_F16    out16 = acc + b                               qkv   (dinov2.cpp:471-474)
 //   EPI_GELU_F16    out16 = gelu_tanh(r16(acc + b))               fc1   (dinov2.cpp:561-567, vec.h:428-457)
-//   EPI_RESID_F32   X    += lambda * (acc + b)                    o-proj / fc2 + LayerScale + residual
+//   EPI_RESID_F32   X    += lambda * (acc + b)   (TMA reduce-add)  o-proj / fc2 + LayerScale + residual
 //                                                                 (dinov2.cpp:546-551,708-714 / 570-573,744-749)
 //   EPI_SWIGLU_F16  out16 = silu(acc_g + b_g) * (acc_u + b_u)     weights_in (dinov2.cpp:582-605); W rows are
 //                                                                 pre-interleaved 128 gate | 128 up per N tile
@@ -47,7 +52,8 @@ template <int BN> struct GemmCfg {
     static constexpr int kBBytes = BN * GEMM_BK * 2;        // 16/32 KB
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment
+    static constexpr int kEpiBytes = GEMM_EPI_WARPS * 4096;   // one 32-row x 128-B staging tile per epilogue warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;   // +1024: manual alignment
     static constexpr int kTmemCols = 512;
 };
 
@@ -65,7 +71,8 @@ __device__ __forceinline__ float silu_f32(float x) {
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     static_assert(EPI != EPI_SWIGLU_F16 || BN == 256, "SwiGLU tiles pair 128 gate + 128 up columns");
     constexpr int kStages = Cfg::kStages;
@@ -74,7 +81,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * Cfg::kStageBytes);
+    uint8_t *smem_epi = smem + kStages * Cfg::kStageBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_epi + Cfg::kEpiBytes);
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -88,11 +96,12 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_k = (p.K + GEMM_BK - 1) / GEMM_BK;
     const int num_tiles = num_m * num_n;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 10 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if constexpr (EPI != EPI_PATCH_F32) prefetch_tmap(&tmC);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 11 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -103,62 +112,85 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    if (warp == 8) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    if (warp == 10) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m_blk = t / num_n, n_blk = t % num_n;
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+        // The whole warp walks the loop (so that addresses and coordinates stay in uniform registers); one elected
+        // lane issues the copies.
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t / num_n, n_blk = t % num_n;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                     // activations are streamed once per N tile (evict first); weights are shared by every CTA
                     tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, kEvictFirst);
                     tma_load_2d_hint(smem_b + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, kEvictLast);
-                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 11) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, 0, 0);
-            int s = 0;
-            uint32_t ph = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aph ^ 1);
+        // All 32 lanes run the control flow and the descriptor arithmetic (warp-uniform -> uniform datapath, no
+        // per-instruction R2UR traffic); a single elected lane issues tcgen05.mma / tcgen05.commit.
+        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, 0, 0);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
-                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
+                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // +32 bytes (16 halves) along K inside the 128-B swizzle atom == +2 in the address field
                         umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
-                    if (++s == kStages) { s = 0; ph ^= 1; }
+                    if (kb == num_k - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 8) {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;    // which half of the tile's columns
+        const int half = warp >> 2;          // which half of the tile's columns
+        uint8_t *stage = smem_epi + warp * 4096;                 // this warp's staging tile (1024-B aligned)
+        uint8_t *stage_row = stage + lane * 128;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);            // 128-B swizzle: chunk c of row r lives at c ^ (r & 7)
+        // the previous TMA store of this warp must have finished reading the staging tile before it is rewritten
+        auto stage_acquire = [&]() {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        };
+        auto stage_release = [&](int c0, int c1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmC, stage, c0, c1);
+                else tma_store_2d(&tmC, stage, c0, c1);
+                bulk_commit();
+            }
+        };
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int m_blk = t / num_n, n_blk = t % num_n;
@@ -166,46 +198,106 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row0 = m_blk * GEMM_BM + q * 32;                   // first row of this warp's 32-row slab
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
             if constexpr (EPI == EPI_SWIGLU_F16) {
-                __half *out = reinterpret_cast<__half *>(p.out);
+                // 64 output columns per warp: gate columns [64 half, +64), up columns 128 + the same
+                const int oc = n_blk * 128 + half * 64;
+                if (oc < p.N / 2) {
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    const int lc = half * 64 + c * 32;                // column inside the 128-wide gate block
-                    uint32_t g[32], u[32];
-                    tmem_ld_32x32b_x32(t_row + lc, g);
-                    tmem_ld_32x32b_x32(t_row + 128 + lc, u);
-                    tmem_ld_wait();
-                    const int ng = n_blk * BN + lc;                   // bias index of the gate column
-                    const int oc = n_blk * 128 + lc;                  // output column
-                    if (row_ok && oc < p.N / 2) {
-                        uint32_t packed[16];
+                    for (int c = 0; c < 2; ++c) {
+                        const int lc = half * 64 + c * 32;
+                        uint32_t g[32], u[32];
+                        tmem_ld_32x32b_x32(t_row + lc, g);
+                        tmem_ld_32x32b_x32(t_row + 128 + lc, u);
+                        tmem_ld_wait();
+                        if (c == 0) stage_acquire();
+                        const int ng = n_blk * BN + lc;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float g0 = __uint_as_float(g[j]) + __ldg(p.bias + ng + j);
-                            const float g1 = __uint_as_float(g[j + 1]) + __ldg(p.bias + ng + j + 1);
-                            const float u0 = __uint_as_float(u[j]) + __ldg(p.bias + ng + 128 + j);
-                            const float u1 = __uint_as_float(u[j + 1]) + __ldg(p.bias + ng + 128 + j + 1);
-                            packed[j >> 1] = pack_half2(silu_f32(g0) * u0, silu_f32(g1) * u1);
+                        for (int v = 0; v < 4; ++v) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const int j = 8 * v + e;
+                                const float g0 = __uint_as_float(g[j]) + __ldg(p.bias + ng + j);
+                                const float g1 = __uint_as_float(g[j + 1]) + __ldg(p.bias + ng + j + 1);
+                                const float u0 = __uint_as_float(u[j]) + __ldg(p.bias + ng + 128 + j);
+                                const float u1 = __uint_as_float(u[j + 1]) + __ldg(p.bias + ng + 128 + j + 1);
+                                pk[e >> 1] = pack_half2(silu_f32(g0) * u0, silu_f32(g1) * u1);
+                            }
+                            *reinterpret_cast<uint4 *>(stage_row + (((c * 4 + v) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        uint4 *dst = reinterpret_cast<uint4 *>(out + static_cast<size_t>(row) * p.ldo + oc);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
                     }
+                    stage_release(oc, row0);
                 }
-            } else {
+            } else if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_GELU_F16) {
+                constexpr int kSteps = BN / 2 / 64;                      // 64 fp16 columns (one 128-B row) per TMA store
+#pragma unroll 1
+                for (int c = 0; c < kSteps; ++c) {
+                    const int lc = half * (BN / 2) + c * 64;
+                    const int col = n_blk * BN + lc;
+                    if (col >= p.N) break;                               // warp-uniform
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(t_row + lc, r0);
+                    tmem_ld_32x32b_x32(t_row + lc + 32, r1);
+                    tmem_ld_wait();
+                    stage_acquire();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const uint32_t *r = v < 4 ? &r0[8 * v] : &r1[8 * (v - 4)];
+                        float x[8];
+                        if (col + 8 * v < p.N) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 8 * v));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 8 * v + 4));
+                            x[0] = __uint_as_float(r[0]) + b0.x; x[1] = __uint_as_float(r[1]) + b0.y;
+                            x[2] = __uint_as_float(r[2]) + b0.z; x[3] = __uint_as_float(r[3]) + b0.w;
+                            x[4] = __uint_as_float(r[4]) + b1.x; x[5] = __uint_as_float(r[5]) + b1.y;
+                            x[6] = __uint_as_float(r[6]) + b1.z; x[7] = __uint_as_float(r[7]) + b1.w;
+                            if constexpr (EPI == EPI_GELU_F16) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) x[e] = gelu_tanh_r16(x[e]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) x[e] = 0.f;      // clipped by the TMA store anyway
+                        }
+                        *reinterpret_cast<uint4 *>(stage_row + ((v ^ sw) << 4)) =
+                            make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+                    }
+                    stage_release(col, row0);
+                }
+            } else if constexpr (EPI == EPI_RESID_F32) {
+                constexpr int kSteps = BN / 2 / 32;                      // 32 fp32 columns (one 128-B row) per TMA reduce
+#pragma unroll 1
+                for (int c = 0; c < kSteps; ++c) {
+                    const int lc = half * (BN / 2) + c * 32;
+                    const int col = n_blk * BN + lc;
+                    if (col >= p.N) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + lc, r);
+                    tmem_ld_wait();
+                    stage_acquire();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col + 4 * v < p.N) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 4 * v));
+                            const float4 ls = __ldg(reinterpret_cast<const float4 *>(p.lscale + col + 4 * v));
+                            y = make_float4((__uint_as_float(r[4 * v + 0]) + b.x) * ls.x, (__uint_as_float(r[4 * v + 1]) + b.y) * ls.y,
+                                            (__uint_as_float(r[4 * v + 2]) + b.z) * ls.z, (__uint_as_float(r[4 * v + 3]) + b.w) * ls.w);
+                        }
+                        *reinterpret_cast<float4 *>(stage_row + ((v ^ sw) << 4)) = y;
+                    }
+                    stage_release(col, row0);                            // X[row0.., col..] += staged tile
+                }
+            } else {   // EPI_PATCH_F32: rows scatter to (image, token) positions, written directly
+                const int row = row0 + lane;
+                const bool row_ok = row < p.M;
+                const int img = row / p.np, pp = row - img * p.np;
+                const size_t orow = static_cast<size_t>(img) * p.ntok + p.tok_off + pp;
+                const float *pos_row = p.pos + static_cast<size_t>(1 + pp) * p.N;
                 constexpr int kChunks = BN / 2 / 32;
-                size_t orow = static_cast<size_t>(row);
-                const float *pos_row = nullptr;
-                if constexpr (EPI == EPI_PATCH_F32) {
-                    const int img = row / p.np, pp = row - img * p.np;
-                    orow = static_cast<size_t>(img) * p.ntok + p.tok_off + pp;
-                    pos_row = p.pos + static_cast<size_t>(1 + pp) * p.N;
-                }
 #pragma unroll 1
                 for (int c = 0; c < kChunks; ++c) {
                     const int lc = half * (BN / 2) + c * 32;
@@ -214,46 +306,14 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld_32x32b_x32(t_row + lc, r);
                     tmem_ld_wait();
                     if (row_ok && col < p.N) {
-                        if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_GELU_F16) {
-                            __half *out = reinterpret_cast<__half *>(p.out);
-                            uint4 *dst = reinterpret_cast<uint4 *>(out + orow * p.ldo + col);
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow * p.ldo + col);
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                if (col + 8 * v < p.N) {
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 8 * v));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 8 * v + 4));
-                                    float x[8] = {__uint_as_float(r[8 * v + 0]) + b0.x, __uint_as_float(r[8 * v + 1]) + b0.y,
-                                                  __uint_as_float(r[8 * v + 2]) + b0.z, __uint_as_float(r[8 * v + 3]) + b0.w,
-                                                  __uint_as_float(r[8 * v + 4]) + b1.x, __uint_as_float(r[8 * v + 5]) + b1.y,
-                                                  __uint_as_float(r[8 * v + 6]) + b1.z, __uint_as_float(r[8 * v + 7]) + b1.w};
-                                    if constexpr (EPI == EPI_GELU_F16) {
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) x[e] = gelu_tanh_r16(x[e]);
-                                    }
-                                    dst[v] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
-                                                        pack_half2(x[6], x[7]));
-                                }
-                            }
-                        } else {
-                            float *out = reinterpret_cast<float *>(p.out);
-                            float4 *dst = reinterpret_cast<float4 *>(out + orow * p.ldo + col);
-#pragma unroll
-                            for (int v = 0; v < 8; ++v) {
-                                if (col + 4 * v < p.N) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 4 * v));
-                                    float4 y = make_float4(__uint_as_float(r[4 * v + 0]) + b.x, __uint_as_float(r[4 * v + 1]) + b.y,
-                                                           __uint_as_float(r[4 * v + 2]) + b.z, __uint_as_float(r[4 * v + 3]) + b.w);
-                                    if constexpr (EPI == EPI_RESID_F32) {
-                                        const float4 ls = __ldg(reinterpret_cast<const float4 *>(p.lscale + col + 4 * v));
-                                        const float4 x = dst[v];
-                                        y = make_float4(fmaf(y.x, ls.x, x.x), fmaf(y.y, ls.y, x.y), fmaf(y.z, ls.z, x.z),
-                                                        fmaf(y.w, ls.w, x.w));
-                                    } else {   // EPI_PATCH_F32
-                                        const float4 pe = __ldg(reinterpret_cast<const float4 *>(pos_row + col + 4 * v));
-                                        y = make_float4(y.x + pe.x, y.y + pe.y, y.z + pe.z, y.w + pe.w);
-                                    }
-                                    dst[v] = y;
-                                }
+                        for (int v = 0; v < 8; ++v) {
+                            if (col + 4 * v < p.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col + 4 * v));
+                                const float4 pe = __ldg(reinterpret_cast<const float4 *>(pos_row + col + 4 * v));
+                                dst[v] = make_float4(__uint_as_float(r[4 * v + 0]) + b.x + pe.x, __uint_as_float(r[4 * v + 1]) + b.y + pe.y,
+                                                     __uint_as_float(r[4 * v + 2]) + b.z + pe.z, __uint_as_float(r[4 * v + 3]) + b.w + pe.w);
                             }
                         }
                     }
@@ -264,11 +324,12 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
+        if (lane == 0) bulk_wait<0>();       // staging smem must outlive the last TMA store; global writes complete
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }

@@ -87,9 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             if (t0 == 0) {
                 t0 = now;
             } else if (now - t0 > 4000000000ull) {   // 4 s: far beyond any legitimate wait in these kernels
-                printf("dino_b200: mbarrier watchdog fired (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-                       blockIdx.z, threadIdx.x, parity);
-                __trap();
+                __trap();                            // no printf here: a call would force spills into hot loops
             }
         }
     }
@@ -121,6 +119,27 @@ __device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+
+
+// 2-D tiled store shared -> global (bulk async-group completion); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// same, but global[...] += smem[...] (element-wise add performed by the memory system)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const void *smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 // Allocate `ncols` (power of two >= 32) TMEM columns; the base address is written to *smem_dst.
@@ -170,6 +189,54 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+
+// 16 / 1 column variants (row sums, narrow accumulators)
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t &r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+// warpgroup-wide register reallocation (all 4 warps of the warpgroup must execute it)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// max(a, b, c) in one instruction (sm_100 FMNMX3)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// {lo, hi} fp32 -> packed f16x2 (round to nearest even)
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// two fp16 exp2 in one MUFU op
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t d;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(x));
+    return d;
+}
+// L2 prefetch of the 128-byte line containing p
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// registers -> TMEM (same lane/column mapping as the loads); complete with tmem_st_wait()
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors

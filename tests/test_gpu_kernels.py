@@ -49,10 +49,15 @@ def test_gemm_gelu_matches_fp16_table_semantics(M, N, K):
     torch.cuda.synchronize()
     v = ref.half().float()
     want = (0.5 * v * (1 + torch.tanh(0.7978845608028654 * v * (1 + 0.044715 * v * v)))).half()
-    # identical up to fp32 accumulation order flipping an fp16 rounding of v: a few one-ulp differences at most
-    ulp_off = (out.view(torch.int16).int() - want.view(torch.int16).int()).abs()
-    assert int(ulp_off.max()) <= 2
-    assert float((ulp_off > 0).float().mean()) < 0.02
+    # The engine evaluates v * sigmoid(2 inner) (no cancellation) where the table evaluates 0.5 v (1 + tanhf(inner)):
+    # identical to within one fp16 rounding except in the deep negative tail, where the table's own 1 + tanh
+    # cancellation noise (|gelu| < 1e-3) shows up as a few ulps of a tiny number.
+    err = (out.float() - want.float()).abs()
+    tol = want.float().abs() * 2.0 ** -9 + 4e-6        # two fp16 ulps (one from v = fp16(x) flipping, one from the result)
+    worst = int((err - tol).argmax())
+    assert bool((err <= tol).all()), (float(err.flatten()[worst]), float(want.flatten()[worst]), float(out.flatten()[worst]),
+                                      float(ref.flatten()[worst]))
+    assert float((err > 0).float().mean()) < 0.02, float((err > 0).float().mean())
     assert nmse_t(out, want) < 1e-7
 
 

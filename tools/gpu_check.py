@@ -213,8 +213,59 @@ def check_bench_quick(args):
     print(f"bench {name} B={B}: {ms:.2f} ms/step  {B / ms * 1000:.1f} img/s  cls finite={bool(torch.isfinite(cls).all())}", flush=True)
 
 
+def check_attn_bench(args):
+    """time the attention kernel alone at the ViT-L bench shape; variant via env DINO_B200_ATTN / _PINGPONG"""
+    import torch
+    from dinov2_b200 import engine as E
+    B, N, D = (int(a) for a in args[:3]) if len(args) >= 3 else (64, 1370, 1024)
+    qkv = torch.randn(B * N, 3 * D, device="cuda").half()
+    out = torch.zeros(B * N, D, device="cuda", dtype=torch.half)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D, st.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        n = 10
+        for _ in range(n):
+            E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D, st.cuda_stream)
+        e1.record(st)
+        st.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    fl = 4.0 * N * N * D * B
+    print(f"attn_bench B={B} N={N} D={D} variant={os.environ.get('DINO_B200_ATTN','3')} pp={os.environ.get('DINO_B200_ATTN_PINGPONG','1')}: "
+          f"{ms*1000:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+def check_gemm_bench(args):
+    """time each GEMM shape of a ViT-L layer alone"""
+    import torch
+    from dinov2_b200 import engine as E
+    M = int(args[0]) if args else 87680
+    st = torch.cuda.Stream()
+    for name, epi, N, K in [("qkv", E.EPI_BIAS_F16, 3072, 1024), ("proj", E.EPI_RESID_F32, 1024, 1024),
+                            ("fc1", E.EPI_GELU_F16, 4096, 1024), ("fc2", E.EPI_RESID_F32, 1024, 4096)]:
+        A = (torch.randn(M, K, device="cuda") * 0.5).half()
+        W = (torch.randn(N, K, device="cuda") * 0.05).half()
+        bias = torch.randn(N, device="cuda") * 0.1
+        ls = torch.rand(N, device="cuda")
+        out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == E.EPI_RESID_F32 else torch.half)
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                E.kernel_gemm(epi, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), out.data_ptr(), N, stream=st.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            n = 10
+            for _ in range(n):
+                E.kernel_gemm(epi, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), out.data_ptr(), N, stream=st.cuda_stream)
+            e1.record(st)
+            st.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"gemm_bench {name} M={M} N={N} K={K}: {ms*1000:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
 CHECKS = {"gemm": check_gemm, "attention": check_attention, "layernorm": check_layernorm, "model_tiny": check_model_tiny,
-          "model_vits": check_model_vits, "bench_quick": check_bench_quick}
+          "model_vits": check_model_vits, "bench_quick": check_bench_quick, "attn_bench": check_attn_bench, "gemm_bench": check_gemm_bench}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
