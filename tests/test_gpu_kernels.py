@@ -53,7 +53,9 @@ def test_gemm_gelu_matches_fp16_table_semantics(M, N, K):
     # identical to within one fp16 rounding except in the deep negative tail, where the table's own 1 + tanh
     # cancellation noise (|gelu| < 1e-3) shows up as a few ulps of a tiny number.
     err = (out.float() - want.float()).abs()
-    tol = want.float().abs() * 2.0 ** -9 + 4e-6        # two fp16 ulps (one from v = fp16(x) flipping, one from the result)
+    # fp32 accumulation order may flip the rounding of v = fp16(x) by one ulp (|v| 2^-10), which moves gelu by up to
+    # |gelu'| <= 1.13 times that; plus one ulp of the fp16 result itself
+    tol = 1.2 * v.abs() * 2.0 ** -10 + want.float().abs() * 2.0 ** -10 + 4e-6
     worst = int((err - tol).argmax())
     assert bool((err <= tol).all()), (float(err.flatten()[worst]), float(want.flatten()[worst]), float(out.flatten()[worst]),
                                       float(ref.flatten()[worst]))
