@@ -94,8 +94,18 @@ static CUtensorMap make_tmap_out(int epi, const void *out, uint64_t cols, uint64
 // ------------------------------------------------------------------------------------------------ launches
 static int g_num_sms = 0;
 
+// DINO_B200_GEMM_CG=1 selects the one-CTA-per-tile GEMM (A/B comparisons); default: CTA pairs (cta_group::2)
+static int gemm_cg() {
+    static int v = [] {
+        const char *e = getenv("DINO_B200_GEMM_CG");
+        return (e && e[0] == '1') ? 1 : 2;
+    }();
+    return v;
+}
+
 template <int BN, int EPI> static void configure_gemm() {
-    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 1>::kSmemBytes));
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 2>::kSmemBytes));
 }
 static void configure_kernels_once() {
     static std::once_flag once;
@@ -129,12 +139,23 @@ static int pick_bn(int epi, int N) {
     return (N % 256 == 0) ? 256 : 128;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
-    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
-    const int grid = std::max(1, std::min(tiles, g_num_sms));
-    gemm_f16_tcgen05<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(tmA, tmB, tmC, p);
-    DINO_CUDA(cudaGetLastError());
+    const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
+    const int grid = std::max(1, std::min(tiles, g_num_sms / CG)) * CG;      // persistent: one CTA (pair) per SM (pair)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmCfg<BN, CG>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DINO_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05<BN, EPI, CG>, tmA, tmB, tmC, p));
 }
 
 // tmC: output map (make_tmap_out) for every epilogue except PATCH, which scatters rows and ignores it
@@ -143,7 +164,7 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
     if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
 #define DINO_GEMM_CASE(bn, e) \
-    if (BN == bn && epi == e) return launch_gemm_t<bn, e>(tmA, tmB, tmC, p, st)
+    if (BN == bn && epi == e) return gemm_cg() == 2 ? launch_gemm_t<bn, e, 2>(tmA, tmB, tmC, p, st) : launch_gemm_t<bn, e, 1>(tmA, tmB, tmC, p, st)
     DINO_GEMM_CASE(256, EPI_BIAS_F16);
     DINO_GEMM_CASE(128, EPI_BIAS_F16);
     DINO_GEMM_CASE(256, EPI_GELU_F16);
@@ -382,7 +403,7 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
     if (d_perm) DINO_CUDA(cudaFree(d_perm));
     L.bias = upload_f32(e, b, N, perm);
     // logical K columns = ldw: the pad columns are real zeros, so the K loop needs no tail case
-    if (want_tmap) L.tm = make_tmap_f16(L.w, L.ldw, N, L.ldw, L.BN);
+    if (want_tmap) L.tm = make_tmap_f16(L.w, L.ldw, N, L.ldw, L.BN / gemm_cg());   // each CTA of a pair loads half the rows
 }
 
 static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) {
@@ -972,7 +993,7 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     configure_kernels_once();
     const int BN = dino::pick_bn(epi, N);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
-    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN);
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN / dino::gemm_cg());
     dino::GemmParams gp{};
     gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = out; gp.ldo = ldo;
     gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = tok_off;

@@ -46,11 +46,15 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
 
-template <int BN> struct GemmCfg {
-    static constexpr int kStages = BN == 256 ? 4 : 6;
-    static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;   // 16 KB
-    static constexpr int kBBytes = BN * GEMM_BK * 2;        // 16/32 KB
+// CG = CTAs per tile: 1 = every CTA computes its own 128 x BN tile; 2 = a CTA pair (cluster of 2, tcgen05 cta_group::2)
+// computes a 256 x BN tile: each CTA loads its 128 A rows and HALF of the BN weight rows, the pair's tensor cores read
+// both halves — per-CTA shared-memory fill and operand-read traffic drop by a third, which is what limits the 1-CTA
+// kernel (48 KB of TMA writes + 48 KB of operand reads per 512 MMA cycles against a 128 B/clk shared-memory port).
+template <int BN, int CG> struct GemmCfg {
+    static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;          // 16 KB
+    static constexpr int kBBytes = (BN / CG) * GEMM_BK * 2;        // this CTA's share of the weight tile
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (192 * 1024) / kStageBytes;     // 4 (BN 256, CG 1) .. 8
     static constexpr int kBarBytes = 256;
     static constexpr int kEpiBytes = GEMM_EPI_WARPS * 4096;   // one 32-row x 128-B staging tile per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;   // +1024: manual alignment
@@ -69,11 +73,12 @@ __device__ __forceinline__ float silu_f32(float x) {
     return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
+    static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
     static_assert(EPI != EPI_SWIGLU_F16 || BN == 256, "SwiGLU tiles pair 128 gate + 128 up columns");
     constexpr int kStages = Cfg::kStages;
 
@@ -91,10 +96,13 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int num_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);       // tiles of 128*CG rows
     const int num_n = (p.N + BN - 1) / BN;
     const int num_k = (p.K + GEMM_BK - 1) / GEMM_BK;
     const int num_tiles = num_m * num_n;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;         // 0 = leader (issues the MMAs)
+    const int tile0 = static_cast<int>(blockIdx.x) / CG;                // first tile of this CTA (pair)
+    const int tile_step = static_cast<int>(gridDim.x) / CG;
 
     if (warp == 10 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -103,18 +111,22 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 11 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], CG);                      // pair: the leader's own expect_tx arrive + the peer's arrive
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+            mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CG);   // pair: the epilogue warps of both CTAs free the accumulator
         }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    if (warp == 8) {
+        if constexpr (CG == 2) tmem_alloc_2sm(tmem_ptr, Cfg::kTmemCols);
+        else tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();                // barrier inits visible to the peer before any remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -124,15 +136,25 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // lane issues the copies.
         int s = 0;
         uint32_t ph = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = tile0; t < num_tiles; t += tile_step) {
             const int m_blk = t / num_n, n_blk = t % num_n;
+            const int row_a = (m_blk * CG + static_cast<int>(cta_rank)) * GEMM_BM;          // this CTA's 128 A rows
+            const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (BN / CG);          // this CTA's share of the weight rows
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                     // activations are streamed once per N tile (evict first); weights are shared by every CTA
-                    tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, kEvictFirst);
-                    tma_load_2d_hint(smem_b + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, kEvictLast);
+                    if constexpr (CG == 2) {
+                        const uint32_t full0 = mapa_shared(&full_bar[s], 0);                 // the leader's barrier counts both CTAs' bytes
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+                        else mbar_arrive_cluster(full0);
+                        tma_load_2d_2sm(smem_a + s * Cfg::kABytes, &tmA, full0, kb * GEMM_BK, row_a, kEvictFirst);
+                        tma_load_2d_2sm(smem_b + s * Cfg::kBBytes, &tmB, full0, kb * GEMM_BK, row_b, kEvictLast);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                        tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, row_a, kEvictFirst);
+                        tma_load_2d_hint(smem_b + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * GEMM_BK, row_b, kEvictLast);
+                    }
                 }
                 __syncwarp();
                 if (++s == kStages) { s = 0; ph ^= 1; }
@@ -142,32 +164,42 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------ MMA issuer
         // All 32 lanes run the control flow and the descriptor arithmetic (warp-uniform -> uniform datapath, no
         // per-instruction R2UR traffic); a single elected lane issues tcgen05.mma / tcgen05.commit.
-        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, 0, 0);
+        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, BN, 0, 0);
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
-            mbar_wait(&tmem_empty[as], aph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
-            for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(&full_bar[s], ph);
+        if (cta_rank == 0) {                                   // pair: only the leader issues; its MMAs drive both tensor cores
+            for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
+                const int as = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aph ^ 1);
                 tc_fence_after();
-                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
-                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        // +32 bytes (16 halves) along K inside the 128-B swizzle atom == +2 in the address field
-                        umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            // +32 bytes (16 halves) along K inside the 128-B swizzle atom == +2 in the address field
+                            if constexpr (CG == 2) umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                            else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        // frees the smem stage (in both CTAs of a pair) once these MMAs retire; after the last k-block the
+                        // accumulator is complete -> epilogue warps (of both CTAs)
+                        if constexpr (CG == 2) {
+                            umma_commit_2sm(&empty_bar[s], 3);
+                            if (kb == num_k - 1) umma_commit_2sm(&tmem_full[as], 3);
+                        } else {
+                            umma_commit(&empty_bar[s]);
+                            if (kb == num_k - 1) umma_commit(&tmem_full[as]);
+                        }
                     }
-                    umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
-                    if (kb == num_k - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+                    __syncwarp();
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp < 8) {
@@ -192,13 +224,13 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         };
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
             const int m_blk = t / num_n, n_blk = t % num_n;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
-            const int row0 = m_blk * GEMM_BM + q * 32;                   // first row of this warp's 32-row slab
+            const int row0 = (m_blk * CG + static_cast<int>(cta_rank)) * GEMM_BM + q * 32;   // first row of this warp's 32-row slab
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
             if constexpr (EPI == EPI_SWIGLU_F16) {
@@ -322,16 +354,21 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));   // the leader's MMA warp waits on it
+                else mbar_arrive(&tmem_empty[as]);
+            }
         }
         if (lane == 0) bulk_wait<0>();       // staging smem must outlive the last TMA store; global writes complete
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();    // the peer may still read this CTA's shared memory / arrive on its barriers
+    else __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
