@@ -25,6 +25,10 @@
 #ifndef AT3_EXP_F32
 #define AT3_EXP_F32 0
 #endif
+// every AT3_POLY_MOD-th pair of probabilities is computed with a polynomial on the FMA pipe instead of MUFU (0 = none)
+#ifndef AT3_POLY_MOD
+#define AT3_POLY_MOD 0   // measured: 0 -> 933 us, 3 -> 950 us, 2 -> 1052 us per ViT-L layer (B=64): MUFU is not the limiter yet
+#endif
 
 namespace dino {
 
@@ -34,6 +38,19 @@ constexpr int AT3_KV_STAGES = 3;
 constexpr int AT3_SMEM_BYTES = 2 * AT3_TILE + AT3_KV_STAGES * 2 * AT3_TILE + 2 * 2 * AT3_TILE + AT3_TILE + 256 + 1024;
 constexpr float AT3_RESCALE_LOG2 = 8.0f;        // lazy-rescale threshold in the exp2 domain
 
+
+// exp2(x) for x <= 0 without the MUFU unit: round-to-nearest split x = n + f (magic-number add), cubic minimax for 2^f on
+// [-0.5, 0.5], exponent field patched by integer add.  Arguments below -30 (masked keys are -inf) clamp to 2^-30, which
+// is zero once P is rounded to fp16.
+__device__ __forceinline__ float exp2_poly3(float x) {
+    const float t = fmaxf(x, -30.0f);
+    const float u = t + 12582912.0f;                 // 1.5 * 2^23: low mantissa bits now hold round(t)
+    const float f = t - (u - 12582912.0f);
+    float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+    p = fmaf(p, f, 0.6932762265205383f);
+    p = fmaf(p, f, 0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(u) << 23));
+}
 
 // Rare path of the lazy running-max correction: scale this warp's 32 rows of O_t (64 numerator columns and the
 // denominator column) in TMEM.  Kept out of line so that its 64 temporaries do not add to the register pressure of
@@ -337,6 +354,7 @@ attention_fwd_v3(const __grid_constant__ CUtensorMap tmQKV, const Attn3Params p)
                     }
                 }
                 const float mc = m_used * c;
+                AT3_SEV(18);
                 if (j > 0) mbar_wait(&o_full[t], (n_tile - 1) & 1);   // P buffer is free once P(j-1) V(j-1) has completed
 
                 // Ping-pong: only one warpgroup at a time is in its MUFU-bound exp phase; the other one meanwhile waits
@@ -364,9 +382,15 @@ attention_fwd_v3(const __grid_constant__ CUtensorMap tmQKV, const Attn3Params p)
 #if AT3_EXP_F32
                         pk[e] = cvt_f16x2(ex2_approx(x0), ex2_approx(x1));     // fp32 exp2, one rounding when packing
 #else
-                        // ex2.approx.f16x2 (two MUFU.EX2.F16 + PRMT in SASS) measured ~6 % faster end to end than fp32
-                        // MUFU.EX2 + pack; the exponent argument (<= 0) is rounded to fp16 first
-                        pk[e] = ex2_f16x2(cvt_f16x2(x0, x1));
+                        if (AT3_POLY_MOD > 0 && ((g * 4 + e) % AT3_POLY_MOD) == AT3_POLY_MOD - 1) {
+                            // this pair is exponentiated on the FMA/ALU pipes (Cody-Waite split + cubic, rel. error 7.7e-5,
+                            // below the fp16 rounding of P) so that the MUFU unit is not the only exp2 engine
+                            pk[e] = cvt_f16x2(exp2_poly3(x0), exp2_poly3(x1));
+                        } else {
+                            // ex2.approx.f16x2 (two MUFU.EX2.F16 + PRMT in SASS); the exponent argument (<= 0) is
+                            // rounded to fp16 first
+                            pk[e] = ex2_f16x2(cvt_f16x2(x0, x1));
+                        }
 #endif
                     }
                     uint8_t *dst = p_row + (g >> 3) * AT3_TILE + (((g & 7) ^ sw) << 4);

@@ -45,6 +45,10 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
+// accumulator column blocks issued round-robin per k-block (1 = one MMA per k-step; 2 and 4 measured no faster)
+#ifndef GEMM_NSPLIT
+#define GEMM_NSPLIT 1
+#endif
 
 // CG = CTAs per tile: 1 = every CTA computes its own 128 x BN tile; 2 = a CTA pair (cluster of 2, tcgen05 cta_group::2)
 // computes a 256 x BN tile: each CTA loads its 128 A rows and HALF of the BN weight rows, the pair's tensor cores read
@@ -164,7 +168,12 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------ MMA issuer
         // All 32 lanes run the control flow and the descriptor arithmetic (warp-uniform -> uniform datapath, no
         // per-instruction R2UR traffic); a single elected lane issues tcgen05.mma / tcgen05.commit.
-        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, BN, 0, 0);
+        // Optionally the tile's accumulator is split into NSPLIT independent column blocks whose MMAs are issued
+        // round-robin (experiment: accumulate-dependent tcgen05.mma do pipeline — splitting bought nothing).
+        constexpr int NSPLIT = GEMM_NSPLIT;
+        constexpr int NSUB = BN / NSPLIT;                                     // accumulator columns per chain
+        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, NSUB, 0, 0);
+        constexpr uint32_t b_sub = (NSUB / CG) * GEMM_BK * 2 / 16;              // descriptor units between the chains' B rows
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
@@ -183,9 +192,14 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / 16; ++k) {
-                            // +32 bytes (16 halves) along K inside the 128-B swizzle atom == +2 in the address field
-                            if constexpr (CG == 2) umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                            else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                            for (int h = 0; h < NSPLIT; ++h) {
+                                // +32 bytes (16 halves) along K inside the 128-B swizzle atom == +2 in the address field
+                                if constexpr (CG == 2)
+                                    umma_f16_ss_2sm(d_tmem + h * NSUB, a_desc + 2 * k, b_desc + h * b_sub + 2 * k, idesc, (kb | k) != 0);
+                                else
+                                    umma_f16_ss(d_tmem + h * NSUB, a_desc + 2 * k, b_desc + h * b_sub + 2 * k, idesc, (kb | k) != 0);
+                            }
                         }
                         // frees the smem stage (in both CTAs of a pair) once these MMAs retire; after the last k-block the
                         // accumulator is complete -> epilogue warps (of both CTAs)

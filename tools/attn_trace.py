@@ -18,7 +18,7 @@ ptr = int(open("/tmp/trace_ptr.txt").read())
 buf = (ctypes.c_uint64 * (3 * 512 * 2))()
 cudart = ctypes.CDLL("libcudart.so.12")
 cudart.cudaMemcpy(buf, ctypes.c_void_p(ptr), ctypes.sizeof(buf), 2)
-names = {5: "kv_full ok", 6: "s_free ok", 7: "p_full ok", 8: "iter top", 9: "mma issued", 1: "S0 issued", 2: "S1 issued", 3: "PV0 issued", 4: "PV1 issued", 10: "wait S", 11: "got S", 12: "S in regs", 13: "max done", 14: "exp start", 15: "exp done", 16: "P stored", 17: "p_full arrived"}
+names = {5: "kv_full ok", 6: "s_free ok", 7: "p_full ok", 8: "iter top", 9: "mma issued", 1: "S0 issued", 2: "S1 issued", 3: "PV0 issued", 4: "PV1 issued", 10: "wait S", 11: "got S", 12: "S in regs", 18: "max done", 13: "o_full ok", 14: "exp start", 15: "exp done", 16: "P stored", 17: "p_full arrived"}
 ev = []
 for role in range(3):
     for i in range(512):

@@ -177,40 +177,55 @@ def check_model_vits(args):
 
 
 def check_bench_quick(args):
+    """device-resident forward timing for any config: bench_quick:<model>:<batch>[:quant]"""
     import numpy as np
     import torch
     import dinov2_b200 as d
     from dinov2_b200 import synth
     name = args[0] if args else "vitl14"
     B = int(args[1]) if len(args) > 1 else 64
+    quant = args[2] if len(args) > 2 and args[2] != "f16" else None
     cfg = synth.CONFIGS[name]
-    path = f"/tmp/dino_w/{name}_f16_0.gguf"
+    path = f"/tmp/dino_w/{name}_{quant or 'f16'}_0.gguf"
     os.makedirs("/tmp/dino_w", exist_ok=True)
+    t0 = time.time()
     if not os.path.exists(path):
-        synth.write_synth_gguf(path, cfg, seed=0)
+        synth.write_synth_gguf(path, cfg, seed=0, quant=quant)
+    t1 = time.time()
     eng = d.Engine(path)
+    t2 = time.time()
     imgs = torch.from_numpy(synth.lcg_batch(0, 2, 518, 518)).cuda()
     imgs = imgs.repeat((B + 1) // 2, 1, 1, 1)[:B].contiguous()
     cls = torch.empty(B, cfg.hidden_size, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    probs = torch.empty(B, cfg.num_classes, device="cuda")
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
     eng.reserve(B, 518, 518)
-    for _ in range(2):
-        eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, False, cls_ptr=cls.data_ptr(), stream=st)
-    torch.cuda.synchronize()
-    eng.set_profiling(True)
-    eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, False, cls_ptr=cls.data_ptr(), stream=st)
-    torch.cuda.synchronize()
-    print("profile", eng.get_profile(), flush=True)
-    eng.set_profiling(False)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n = 5
-    for _ in range(n):
-        eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, False, cls_ptr=cls.data_ptr(), stream=st)
-    e1.record()
-    torch.cuda.synchronize()
+    n_tok = 1 + cfg.num_register_tokens + 37 * 37
+    D, L = cfg.hidden_size, cfg.num_hidden_layers
+    gflop = (L * (2 * n_tok * D * 3 * D + 2 * n_tok * D * D + 2 * n_tok * D * (cfg.mlp_in + cfg.mlp_hidden) + 4 * n_tok * n_tok * D)
+             + 2 * 1369 * 588 * D) / 1e9
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, True, cls_ptr=cls.data_ptr(), probs_ptr=probs.data_ptr(), stream=st)
+        stream.synchronize()
+        eng.set_profiling(True)
+        eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, True, cls_ptr=cls.data_ptr(), probs_ptr=probs.data_ptr(), stream=st)
+        stream.synchronize()
+        prof = eng.get_profile()
+        eng.set_profiling(False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n = 5
+        for _ in range(n):
+            eng.forward_device(imgs.data_ptr(), 1, B, 518, 518, True, cls_ptr=cls.data_ptr(), probs_ptr=probs.data_ptr(), stream=st)
+        e1.record(stream)
+        stream.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(f"bench {name} B={B}: {ms:.2f} ms/step  {B / ms * 1000:.1f} img/s  cls finite={bool(torch.isfinite(cls).all())}", flush=True)
+    ok = bool(torch.isfinite(cls).all()) and bool(torch.isfinite(probs).all()) and bool(((probs.sum(1) - 1).abs() < 1e-4).all())
+    print(f"bench {name} quant={quant} B={B}: gguf {t1 - t0:.1f}s load {t2 - t1:.1f}s | {ms:.2f} ms/step  {B / ms * 1000:.1f} img/s  "
+          f"{gflop * B / ms:.0f} TFLOP/s ({gflop * B / ms / 1676.0 * 100:.1f}% of burst roofline)  outputs ok={ok}", flush=True)
+    print("  profile(ms)", {k: round(v, 2) for k, v in prof.items()}, flush=True)
 
 
 def check_attn_bench(args):
