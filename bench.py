@@ -140,6 +140,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--features", action="store_true", help="feature-extraction mode (patch tokens) instead of classify")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="none", choices=["none", "cls", "patch"],
+                    help="all-gather the per-image features across ranks inside the timed step (NCCL over NVLink)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,11 +212,18 @@ def main():
     else:
         host_out["patch_tokens"] = torch.empty(B, NP, D).pin_memory().numpy()
     stream = torch.cuda.Stream()
+    gathered = None
+    if world > 1 and args.gather != "none":
+        from dinov2_b200 import dp
+        src = dev_cls if args.gather == "cls" or dev_patch is None else dev_patch
+        gathered = torch.empty((B * world,) + tuple(src.shape[1:]), device="cuda")
 
     def step_device():
         eng.forward_device(dev_in.data_ptr(), d.LAYOUT_BGR_HWC, B, H, W, classify, cls_ptr=dev_cls.data_ptr(),
                            patch_ptr=dev_patch.data_ptr() if dev_patch is not None else 0,
                            probs_ptr=dev_probs.data_ptr() if dev_probs is not None else 0, stream=stream.cuda_stream)
+        if gathered is not None:      # the only exchange of the path: every rank ends up with the whole batch's features
+            dist.all_gather_into_tensor(gathered, dev_cls if args.gather == "cls" or dev_patch is None else dev_patch)
 
     def step_host():
         eng.forward(host_in.numpy(), classify=classify, layout=d.LAYOUT_BGR_HWC, want_patch=not classify, out=host_out)
@@ -285,7 +294,7 @@ def main():
             "data": "synthetic (LCG images, seeded random-init weights in the reference converter's GGUF manifest)",
             "config": {"workload": workload, "tokens_per_image": n_tok, "gflop_per_image": fl["total"] / 1e9,
                        "l2_policy": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world}", "outputs_finite": finite},
+                       "parallelism": f"dp{world}", "feature_all_gather": args.gather, "outputs_finite": finite},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},

@@ -273,4 +273,54 @@ __global__ void pos_embed_bicubic_kernel(const float *__restrict__ pos, float *_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Image preprocessing on device (reference dino_preprocess / dino_classify_preprocess, dinov2.cpp:106-156):
+// u8 BGR HWC -> float (x * 1/255) -> cv::resize(INTER_CUBIC) to (RH, RW) -> optional centre crop (OH, OW at offset
+// cy, cx) -> per-channel (v - mean) / std, output float BGR HWC (what dino_predict consumes).  Same OpenCV sampling
+// convention and summation order (horizontal taps first, then vertical) as pos_embed_bicubic_kernel.
+// One thread per output pixel (3 channels).
+__global__ void preprocess_bicubic_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst, int B, int H, int W, int RH,
+                                          int RW, int OH, int OW, int cy, int cx, float3 mean_bgr, float3 inv_std_bgr) {
+    const long long total = static_cast<long long>(B) * OH * OW;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % OW);
+        const int oy = static_cast<int>((idx / OW) % OH);
+        const int b = static_cast<int>(idx / (static_cast<long long>(OW) * OH));
+        const int ry = oy + cy, rx = ox + cx;                       // coordinates in the resized image
+        const float fy = static_cast<float>((ry + 0.5) * (static_cast<double>(H) / RH) - 0.5);
+        const float fx = static_cast<float>((rx + 0.5) * (static_cast<double>(W) / RW) - 0.5);
+        const int sy = static_cast<int>(floorf(fy)), sx = static_cast<int>(floorf(fx));
+        float wy[4], wx[4];
+        cubic_w(fy - sy, wy);
+        cubic_w(fx - sx, wx);
+        int iy[4], ix[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            iy[k] = min(max(sy - 1 + k, 0), H - 1);
+            ix[k] = min(max(sx - 1 + k, 0), W - 1);
+        }
+        const uint8_t *img = src + static_cast<size_t>(b) * H * W * 3;
+        float acc[3] = {0.f, 0.f, 0.f};
+        const float s255 = static_cast<float>(1.0 / 255.0);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const uint8_t *row = img + static_cast<size_t>(iy[a]) * W * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float h = (static_cast<float>(row[ix[0] * 3 + c]) * s255) * wx[0];
+                h += (static_cast<float>(row[ix[1] * 3 + c]) * s255) * wx[1];
+                h += (static_cast<float>(row[ix[2] * 3 + c]) * s255) * wx[2];
+                h += (static_cast<float>(row[ix[3] * 3 + c]) * s255) * wx[3];
+                acc[c] = a == 0 ? h * wy[0] : acc[c] + h * wy[a];
+            }
+        }
+        float *o = dst + idx * 3;
+        o[0] = (acc[0] - mean_bgr.x) * inv_std_bgr.x;
+        o[1] = (acc[1] - mean_bgr.y) * inv_std_bgr.y;
+        o[2] = (acc[2] - mean_bgr.z) * inv_std_bgr.z;
+    }
+}
+
 }  // namespace dino

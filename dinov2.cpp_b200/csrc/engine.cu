@@ -287,6 +287,8 @@ struct dino_b200_engine {
     // host-API output staging in device memory
     float *o_cls = nullptr, *o_patch = nullptr;
     size_t cap_o_patch = 0;
+    uint8_t *d_u8 = nullptr;          // raw frames for on-device preprocessing
+    size_t cap_u8 = 0;
 
     uint64_t launches = 0;
     bool profiling = false;
@@ -844,6 +846,7 @@ void dino_b200_destroy(dino_b200_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     dino::free_arena(e);
     for (void *p : e->allocs) cudaFree(p);
+    if (e->d_u8) cudaFree(e->d_u8);
     for (auto &pe : e->prof) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto &pe : e->prof_pool) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -1028,3 +1031,94 @@ dino_b200_status dino_b200_kernel_layernorm(const float *X, const float *gamma, 
 }
 
 }  // extern "C"
+
+namespace dino {
+// runs the preprocessing kernel: frames already in e->d_u8, result in e->d_img; returns output size
+static void preprocess_device(dino_b200_engine *e, int B, int H, int W, bool classify, int &OH, int &OW) {
+    const int ps = e->hp.patch_size;
+    int RH, RW, cy = 0, cx = 0;
+    if (classify) {
+        RH = RW = 256;
+        OH = OW = 224;
+        cy = (RH - OH) / 2;
+        cx = (RW - OW) / 2;
+    } else {
+        RW = (W / ps + 1) * ps;
+        RH = (H / ps + 1) * ps;
+        OH = RH;
+        OW = RW;
+    }
+    ensure_arena(e, B, OH, OW);
+    // IMAGENET mean / std are R,G,B (reference dinov2.h:16-17); the image is B,G,R
+    const float3 mean = make_float3(0.406f, 0.456f, 0.485f);
+    const float3 inv_std = make_float3(1.0f / 0.225f, 1.0f / 0.224f, 1.0f / 0.229f);
+    const long long total = static_cast<long long>(B) * OH * OW;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(g_num_sms) * 32));
+    preprocess_bicubic_kernel<<<grid, 256, 0, e->stream>>>(e->d_u8, e->d_img, B, H, W, RH, RW, OH, OW, cy, cx, mean, inv_std);
+    DINO_CUDA(cudaGetLastError());
+    e->launches++;
+}
+
+static void upload_frames(dino_b200_engine *e, const uint8_t *images, int B, int H, int W) {
+    const size_t bytes = static_cast<size_t>(B) * H * W * 3;
+    if (bytes > e->cap_u8) {
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->d_u8) DINO_CUDA(cudaFree(e->d_u8));
+        e->d_u8 = nullptr;
+        e->cap_u8 = 0;
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->d_u8), bytes));
+        e->cap_u8 = bytes;
+    }
+    DINO_CUDA(cudaMemcpyAsync(e->d_u8, images, bytes, cudaMemcpyHostToDevice, e->stream));
+}
+}  // namespace dino
+
+extern "C" dino_b200_status dino_b200_preprocess(dino_b200_engine *e, const uint8_t *images, int B, int H, int W, int classify,
+                                                 float *out, int *out_h, int *out_w) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "preprocess: bad batch or image size");
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::upload_frames(e, images, B, H, W);
+    int OH = 0, OW = 0;
+    dino::preprocess_device(e, B, H, W, classify != 0, OH, OW);
+    if (out) DINO_CUDA(cudaMemcpyAsync(out, e->d_img, static_cast<size_t>(B) * OH * OW * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    if (out_h) *out_h = OH;
+    if (out_w) *out_w = OW;
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+extern "C" dino_b200_status dino_b200_forward_u8(dino_b200_engine *e, const uint8_t *images, int B, int H, int W, int flags, float *cls,
+                                                 float *patch, float *logits, float *probs) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "forward_u8: bad batch or image size");
+    DINO_CUDA(cudaSetDevice(e->device));
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    dino::upload_frames(e, images, B, H, W);
+    int OH = 0, OW = 0;
+    dino::preprocess_device(e, B, H, W, classify, OH, OW);
+    const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
+    const size_t np = static_cast<size_t>(OH / ps) * (OW / ps);
+    if (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch) {
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->o_patch) DINO_CUDA(cudaFree(e->o_patch));
+        e->o_patch = nullptr;
+        e->cap_o_patch = 0;
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->o_patch), static_cast<size_t>(B) * np * D * sizeof(float)));
+        e->cap_o_patch = static_cast<size_t>(B) * np * D;
+    }
+    cudaStream_t st = e->stream;
+    dino::forward_device(e, e->d_img, DINO_B200_LAYOUT_BGR_HWC, B, OH, OW, flags, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
+                         (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
+    if (cls) DINO_CUDA(cudaMemcpyAsync(cls, e->o_cls, static_cast<size_t>(B) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (patch) DINO_CUDA(cudaMemcpyAsync(patch, e->o_patch, static_cast<size_t>(B) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs, e->probs, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DINO_CUDA(cudaStreamSynchronize(st));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "dino_b200_get_pos_embed", "dino_b200_forward", "dino_b200_forward_device", "dino_b200_synchronize",
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
     "dino_b200_kernel_gemm", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
+    "dino_b200_preprocess", "dino_b200_forward_u8",
 ]
 
 
@@ -71,6 +72,8 @@ def load_library() -> C.CDLL:
     L.dino_b200_forward.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_forward_device.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp, vp]
     L.dino_b200_synchronize.argtypes = [vp]
+    L.dino_b200_preprocess.argtypes = [vp, vp, ip, ip, ip, ip, fp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dino_b200_forward_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_last_error.argtypes = [vp]
     L.dino_b200_last_error.restype = C.c_char_p
     L.dino_b200_kernel_launches.argtypes = [vp]
@@ -197,6 +200,46 @@ class Engine:
             self._h, images.ctypes.data, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
             _host_ptr(res.get("cls")), _host_ptr(res.get("patch_tokens")),
             _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))), self._h)
+        return res
+
+    def preprocess_size(self, H: int, W: int, classify: bool):
+        """Output size of the reference's preprocessing for an H x W frame (dinov2.cpp:111-116, 140-141)."""
+        if classify:
+            return 224, 224
+        ps = self.patch_size
+        return (H // ps + 1) * ps, (W // ps + 1) * ps
+
+    def preprocess(self, frames_u8: np.ndarray, classify: bool = False) -> np.ndarray:
+        """uint8 BGR frames [B,H,W,3] -> float32 [B,OH,OW,3] (device version of dino_preprocess / dino_classify_preprocess)."""
+        frames = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        B, H, W, ch = frames.shape
+        assert ch == 3
+        OH, OW = self.preprocess_size(H, W, classify)
+        out = np.empty((B, OH, OW, 3), np.float32)
+        oh, ow = C.c_int(), C.c_int()
+        _check(load_library().dino_b200_preprocess(self._h, frames.ctypes.data, B, H, W, int(classify), out.ctypes.data,
+                                                   C.byref(oh), C.byref(ow)), self._h)
+        assert (oh.value, ow.value) == (OH, OW)
+        return out
+
+    def forward_u8(self, frames_u8: np.ndarray, classify: bool = False, want_patch: bool = True, want_cls: bool = True
+                   ) -> Dict[str, np.ndarray]:
+        """Raw uint8 BGR frames in, results out: preprocessing and forward pass both on the device."""
+        frames = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        B, H, W, ch = frames.shape
+        assert ch == 3
+        OH, OW = self.preprocess_size(H, W, classify)
+        res: Dict[str, np.ndarray] = {}
+        if want_cls:
+            res["cls"] = np.empty((B, self.hidden_size), np.float32)
+        if want_patch:
+            res["patch_tokens"] = np.empty((B, self.n_patches(OH, OW), self.hidden_size), np.float32)
+        if classify:
+            res["logits"] = np.empty((B, self.num_classes), np.float32)
+            res["probs"] = np.empty((B, self.num_classes), np.float32)
+        _check(load_library().dino_b200_forward_u8(
+            self._h, frames.ctypes.data, B, H, W, FLAG_CLASSIFY if classify else 0, _host_ptr(res.get("cls")),
+            _host_ptr(res.get("patch_tokens")), _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))), self._h)
         return res
 
     def forward_device(self, images_ptr: int, layout: int, B: int, H: int, W: int, classify: bool = False,

@@ -133,6 +133,22 @@ DINO_B200_API dino_b200_status dino_b200_forward_device(dino_b200_engine *e, con
                                                         int W, int flags, float *cls, float *patch, float *logits,
                                                         float *probs, void *stream);
 
+/* "Next row" of the hot path: the reference's host-side OpenCV preprocessing on the device.
+ * images: B raw frames, uint8 BGR interleaved [B][H][W][3] in HOST memory (what cv::imread / VideoCapture deliver).
+ * classify == 0 replaces dino_preprocess (dinov2.cpp:135-156): x/255, bicubic resize UP to the next patch multiple
+ *   ((W/ps+1)*ps x (H/ps+1)*ps, even when already a multiple), per-channel (v - mean)/std.
+ * classify != 0 replaces dino_classify_preprocess (dinov2.cpp:106-132): x/255, bicubic squash to 256x256, centre crop
+ *   224x224, standardise.
+ * The result (float32 BGR [B][out_h][out_w][3]) stays on the device for dino_b200_forward_preprocessed and is
+ * optionally copied to `out` (host, may be NULL). */
+DINO_B200_API dino_b200_status dino_b200_preprocess(dino_b200_engine *e, const uint8_t *images, int B, int H, int W, int classify,
+                                                    float *out, int *out_h, int *out_w);
+
+/* dino_preprocess / dino_classify_preprocess + dino_predict in one call on raw uint8 frames (host in, host out):
+ * what inference.cpp:48-65 does per image, batched.  Preprocessing mode follows DINO_B200_CLASSIFY in flags. */
+DINO_B200_API dino_b200_status dino_b200_forward_u8(dino_b200_engine *e, const uint8_t *images, int B, int H, int W, int flags,
+                                                    float *cls, float *patch, float *logits, float *probs);
+
 /* Replaces ggml_backend_synchronize (inference.cpp:62,66). */
 DINO_B200_API dino_b200_status dino_b200_synchronize(dino_b200_engine *e);
 

@@ -51,3 +51,8 @@ for tag, path in (("f16", f16), ("q8", q8)):
     R.close()
 np.savez_compressed(os.path.join(HERE, "golden.npz"), **out)
 print({k: v.shape for k, v in out.items()})
+
+# ---- preprocessing goldens come from REAL OpenCV (the Python cv2 wheel, 4.13), not from the shim:
+#   rng = np.random.default_rng(7); img = rng.integers(0, 256, (61, 83, 3), uint8)   (BGR)
+#   f = img.astype(float32) * float32(1/255); feat = (cv2.resize(f, (84, 70), INTER_CUBIC) - mean_bgr) / std_bgr
+#   cls = (cv2.resize(f, (256, 256), INTER_CUBIC)[16:240, 16:240] - mean_bgr) / std_bgr      -> preprocess_cv2.npz
