@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -127,6 +128,7 @@ static void configure_kernels_once() {
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -178,13 +180,27 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=1|2 selects an earlier generation of the attention kernel for A/B comparisons (default: 3).
+// DINO_B200_ATTN=1|2|3 selects an earlier generation of the attention kernel for A/B comparisons (default: 4).
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 3;
+        return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 4;
     }();
     return v;
+}
+
+static unsigned long long *attention_trace_buffer(cudaStream_t st) {
+    static unsigned long long *tr = nullptr;
+    if (!tr) cudaMalloc(&tr, 3 * 512 * 2 * 8);
+    cudaMemsetAsync(tr, 0, 3 * 512 * 2 * 8, st);
+    if (const char *f = getenv("DINO_B200_TRACE_PTR")) {
+        FILE *fp = fopen(f, "w");
+        if (fp) {
+            fprintf(fp, "%llu\n", (unsigned long long) tr);
+            fclose(fp);
+        }
+    }
+    return tr;
 }
 
 static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, cudaStream_t st) {
@@ -205,6 +221,21 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.scale_log2 = scale_log2;
         const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
         attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 4) {
+        Attn4Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        ap.trace = nullptr;
+#ifdef AT4_TRACE
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        attention_fwd_v4<<<grid, AT4_THREADS, AT4_SMEM_BYTES, st>>>(tmQKV, ap);
     } else {
         Attn3Params ap;
         ap.n_tok = n_tok;
@@ -218,13 +249,7 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.pingpong = pingpong;
         ap.trace = nullptr;
 #ifdef AT3_TRACE
-        {
-            static unsigned long long *tr = nullptr;
-            if (!tr) { cudaMalloc(&tr, 3 * 512 * 2 * 8); }
-            cudaMemsetAsync(tr, 0, 3 * 512 * 2 * 8, st);
-            ap.trace = tr;
-            if (const char *f = getenv("DINO_B200_TRACE_PTR")) { FILE *fp = fopen(f, "w"); if (fp) { fprintf(fp, "%llu\n", (unsigned long long) tr); fclose(fp); } }
-        }
+        ap.trace = attention_trace_buffer(st);
 #endif
         static const int grid_mult = [] { const char *e = getenv("DINO_B200_ATTN_GRID"); return e ? atoi(e) : 1; }();
         const int grid = grid_mult <= 0 ? ap.num_items : std::max(1, std::min(ap.num_items, g_num_sms * grid_mult));

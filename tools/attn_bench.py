@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Attention kernel alone: numerics vs torch fp32 and time per call (CUDA events) at the ViT-L bench shape.
+usage: python tools/attn_bench.py [lib.so ...]   (DINO_B200_ATTN=3 selects the previous generation)"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import dinov2_b200
+from dinov2_b200 import engine as E
+if len(sys.argv) > 1:
+    E.LIB_PATH = os.path.abspath(sys.argv[1])
+torch.manual_seed(0)
+for (B, N, D) in [(2, 200, 128), (2, 1370, 384), (3, 1374, 128)]:
+    H = D // 64
+    qkv = torch.randn(B * N, 3 * D, device="cuda").half()
+    out = torch.zeros(B * N, D, device="cuda", dtype=torch.half)
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    q, k, v = [t.view(B, N, H, 64).permute(0, 2, 1, 3) for t in qkv.float().split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+    d = (out.float() - ref).abs()
+    print(f"check B={B} N={N} D={D}: max_abs {float(d.max()):.3e} nmse {float(((out.float()-ref)**2).sum()/(ref**2).sum()):.3e}", flush=True)
+B, N, D = 64, 1370, 1024
+# scores with a realistic spread (q.k/8 ~ N(0, 1)): unit-variance q and k
+qkv = torch.randn(B * N, 3 * D, device="cuda").half()
+out = torch.zeros(B * N, D, device="cuda", dtype=torch.half)
+for _ in range(3):
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+iters = 20
+a.record()
+for _ in range(iters):
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / iters
+fl = 4.0 * N * N * D * B
+print(f"attention B={B} N={N} D={D}: {ms*1000:.1f} us/call  {fl/ms/1e9:.1f} TFLOP/s  lib={os.path.basename(E.LIB_PATH)} variant={os.environ.get('DINO_B200_ATTN','default')}", flush=True)
