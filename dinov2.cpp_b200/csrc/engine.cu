@@ -9,6 +9,7 @@
 #include "attention2.cuh"
 #include "attention3.cuh"
 #include "attention4.cuh"
+#include "attention5.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -129,6 +130,7 @@ static void configure_kernels_once() {
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -180,11 +182,11 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=1|2|3 selects an earlier generation of the attention kernel for A/B comparisons (default: 4).
+// DINO_B200_ATTN=1|2|3|4 selects an earlier generation of the attention kernel for A/B comparisons (default: 5).
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 4;
+        return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 5;
     }();
     return v;
 }
@@ -221,6 +223,21 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.scale_log2 = scale_log2;
         const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
         attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 5) {
+        Attn5Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        ap.trace = nullptr;
+#ifdef AT5_TRACE
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        attention_fwd_v5<<<grid, AT5_THREADS, AT5_SMEM_BYTES, st>>>(tmQKV, ap);
     } else if (attention_variant() == 4) {
         Attn4Params ap;
         ap.n_tok = n_tok;

@@ -356,6 +356,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// volatile flavour: keeps its program order relative to other volatile asm (tcgen05.st ...), which stops ptxas from
+// hoisting a whole tile's worth of MUFU results into registers (and spilling them)
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
