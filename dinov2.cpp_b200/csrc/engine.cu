@@ -10,6 +10,7 @@
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention5.cuh"
+#include "attention6.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -131,6 +132,7 @@ static void configure_kernels_once() {
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, AT6_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -146,7 +148,10 @@ static int pick_bn(int epi, int N) {
 template <int BN, int EPI, int CG>
 static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
     const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
-    const int grid = std::max(1, std::min(tiles, g_num_sms / CG)) * CG;      // persistent: one CTA (pair) per SM (pair)
+    // DINO_B200_GEMM_SMS=n restricts the persistent grid to n SMs (experiments: per-SM throughput vs L2 bandwidth share)
+    static const int sm_cap = [] { const char *e = getenv("DINO_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();
+    const int sms = sm_cap > 0 ? std::min(sm_cap, g_num_sms) : g_num_sms;
+    const int grid = std::max(1, std::min(tiles, sms / CG)) * CG;      // persistent: one CTA (pair) per SM (pair)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -182,11 +187,12 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=1|2|3|4 selects an earlier generation of the attention kernel for A/B comparisons (default: 5).
+// DINO_B200_ATTN=1|2|3|4|6 selects another generation of the attention kernel for A/B comparisons (default: 5;
+// 6 = the 16-softmax-warp experiment, measured slower: 872 vs 828 us per ViT-L layer at batch 64).
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 5;
+        return (e && e[0] >= '1' && e[0] <= '6' && e[0] != '5') ? e[0] - '0' : 5;
     }();
     return v;
 }
@@ -223,6 +229,21 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.scale_log2 = scale_log2;
         const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
         attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 6) {
+        Attn6Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        ap.trace = nullptr;
+#ifdef AT6_TRACE
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        attention_fwd_v6<<<grid, AT6_THREADS, AT6_SMEM_BYTES, st>>>(tmQKV, ap);
     } else if (attention_variant() == 5) {
         Attn5Params ap;
         ap.n_tok = n_tok;

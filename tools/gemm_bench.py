@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""GEMM kernel alone at the ViT-L bench shapes: time per call (CUDA events) and TFLOP/s.
+usage: python tools/gemm_bench.py [lib.so]     env DINO_B200_GEMM_SMS / DINO_B200_GEMM_CG select experiments"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import dinov2_b200
+from dinov2_b200 import engine as E
+if len(sys.argv) > 1:
+    E.LIB_PATH = os.path.abspath(sys.argv[1])
+torch.manual_seed(0)
+M = 64 * 1370
+shapes = [("qkv", E.EPI_BIAS_F16, 3072, 1024), ("proj", E.EPI_RESID_F32, 1024, 1024), ("fc1", E.EPI_GELU_F16, 4096, 1024), ("fc2", E.EPI_RESID_F32, 1024, 4096)]
+tag = f"sms={os.environ.get('DINO_B200_GEMM_SMS','all')} cg={os.environ.get('DINO_B200_GEMM_CG','2')} lib={os.path.basename(E.LIB_PATH)}"
+for name, epi, N, K in shapes:
+    A = (torch.randn(M, K, device="cuda") * 0.5).half()
+    W = (torch.randn(N, K, device="cuda") * 0.05).half()
+    bias = torch.randn(N, device="cuda") * 0.1
+    ls = torch.rand(N, device="cuda") + 0.3
+    f32 = epi == E.EPI_RESID_F32
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if f32 else torch.half)
+    def run():
+        E.kernel_gemm(epi, A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr() if f32 else 0, out.data_ptr(), N)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    if name == "qkv":
+        ref = (A[:512].float() @ W.float().t() + bias)
+        print(f"check {name}: max_abs {float((out[:512].float() - ref).abs().max()):.3e}", flush=True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    a.record()
+    for _ in range(iters):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    print(f"gemm {name:5s} M={M} N={N} K={K}: {ms*1000:7.1f} us  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s   [{tag}]", flush=True)
