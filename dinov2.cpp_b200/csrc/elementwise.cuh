@@ -3,6 +3,7 @@
 // streaming (16-byte vector accesses, one warp per token row, grids that cover every SM).
 #pragma once
 #include "ptx.cuh"
+#include "ln_row.cuh"
 
 namespace dino {
 
@@ -54,12 +55,7 @@ __global__ void prefix_tokens_kernel(float *__restrict__ X, const float *__restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm over the hidden dimension, one warp per token (reference ggml_norm, ops.cpp:3109-3158:
-// mean, then centred variance, y = (x-mean)/sqrt(var+eps); followed by *weight + bias, dinov2.cpp:694-700).
-// OUT_HALF: writes the fp16 A operand of the next GEMM (the reference rounds it to fp16 inside mul_mat).
-// D <= 32 * 4 * LN_MAX_V4.
-constexpr int LN_MAX_V4 = 12;   // D up to 1536
-
+// LayerNorm over the hidden dimension, one warp per token (arithmetic in ln_row.cuh).
 template <bool OUT_HALF>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -67,51 +63,9 @@ layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, c
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const int nv = D >> 2;   // float4 per row
-    const float4 *x4 = reinterpret_cast<const float4 *>(X + static_cast<size_t>(warp) * D);
-    float4 v[LN_MAX_V4];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < nv) {
-            v[i] = x4[idx];
-            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / static_cast<float>(D);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < nv) {
-            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = 1.0f / sqrtf(sq / static_cast<float>(D) + eps);
-    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
-    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
-#pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < nv) {
-            const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
-            const float y0 = (v[i].x * rstd) * g.x + b.x, y1 = (v[i].y * rstd) * g.y + b.y;
-            const float y2 = (v[i].z * rstd) * g.z + b.z, y3 = (v[i].w * rstd) * g.w + b.w;
-            if constexpr (OUT_HALF) {
-                uint2 *o2 = reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(out) + static_cast<size_t>(warp) * D);
-                o2[idx] = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
-            } else {
-                float4 *o4 = reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + static_cast<size_t>(warp) * D);
-                o4[idx] = make_float4(y0, y1, y2, y3);
-            }
-        }
-    }
+    const size_t off = static_cast<size_t>(warp) * D;
+    void *orow = OUT_HALF ? static_cast<void *>(reinterpret_cast<__half *>(out) + off) : static_cast<void *>(reinterpret_cast<float *>(out) + off);
+    layernorm_row<OUT_HALF, false>(X + off, gamma, beta, orow, D, eps, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include "attention4.cuh"
 #include "attention5.cuh"
 #include "attention6.cuh"
+#include "attention7.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -91,7 +92,7 @@ static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, 
 }
 // output map of a GEMM epilogue: 32-row x 128-B boxes (one per epilogue warp and step)
 static CUtensorMap make_tmap_out(int epi, const void *out, uint64_t cols, uint64_t rows, uint64_t ld) {
-    return make_tmap_2d(out, epi == EPI_RESID_F32, cols, rows, ld, 32);
+    return make_tmap_2d(out, epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32, cols, rows, ld, 32);
 }
 
 // ------------------------------------------------------------------------------------------------ launches
@@ -124,6 +125,8 @@ static void configure_kernels_once() {
             configure_gemm<128, EPI_GELU_F16>();
             configure_gemm<256, EPI_RESID_F32>();
             configure_gemm<128, EPI_RESID_F32>();
+            configure_gemm<256, EPI_RESID_LN_F32>();
+            configure_gemm<128, EPI_RESID_LN_F32>();
             configure_gemm<256, EPI_SWIGLU_F16>();
             configure_gemm<256, EPI_PATCH_F32>();
             configure_gemm<128, EPI_PATCH_F32>();
@@ -133,6 +136,7 @@ static void configure_kernels_once() {
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, AT6_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -180,6 +184,8 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     DINO_GEMM_CASE(128, EPI_GELU_F16);
     DINO_GEMM_CASE(256, EPI_RESID_F32);
     DINO_GEMM_CASE(128, EPI_RESID_F32);
+    DINO_GEMM_CASE(256, EPI_RESID_LN_F32);
+    DINO_GEMM_CASE(128, EPI_RESID_LN_F32);
     DINO_GEMM_CASE(256, EPI_SWIGLU_F16);
     DINO_GEMM_CASE(256, EPI_PATCH_F32);
     DINO_GEMM_CASE(128, EPI_PATCH_F32);
@@ -192,7 +198,7 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && e[0] >= '1' && e[0] <= '6' && e[0] != '5') ? e[0] - '0' : 5;
+        return (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 5;
     }();
     return v;
 }
@@ -229,6 +235,21 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.scale_log2 = scale_log2;
         const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
         attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 7) {
+        Attn7Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        ap.trace = nullptr;
+#ifdef AT7_TRACE
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        attention_fwd_v7<<<grid, AT7_THREADS, AT7_SMEM_BYTES, st>>>(tmQKV, ap);
     } else if (attention_variant() == 6) {
         Attn6Params ap;
         ap.n_tok = n_tok;
@@ -350,6 +371,7 @@ struct dino_b200_engine {
     // host-API output staging in device memory
     float *o_cls = nullptr, *o_patch = nullptr;
     size_t cap_o_patch = 0;
+    int *ln_count = nullptr;          // per-128-row-block tile counters of the fused residual-GEMM + LayerNorm epilogue
     uint8_t *d_u8 = nullptr;          // raw frames for on-device preprocessing
     size_t cap_u8 = 0;
 
@@ -545,11 +567,12 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
 
 // ------------------------------------------------------------------------------------------------ arena
 static void free_arena(dino_b200_engine *e) {
-    void *ptrs[] = {e->d_img, e->X, e->Y, e->feat, e->logits, e->probs, e->Ape, e->Xn, e->QKV, e->AO, e->H1, e->o_cls, e->o_patch};
+    void *ptrs[] = {e->d_img, e->X, e->Y, e->feat, e->logits, e->probs, e->Ape, e->Xn, e->QKV, e->AO, e->H1, e->o_cls, e->o_patch, e->ln_count};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     e->d_img = e->X = e->Y = e->feat = e->logits = e->probs = e->o_cls = e->o_patch = nullptr;
     e->Ape = e->Xn = e->QKV = e->AO = e->H1 = nullptr;
+    e->ln_count = nullptr;
     e->cap_tok = e->cap_patch = e->cap_img = e->cap_batch = e->cap_o_patch = 0;
 }
 
@@ -582,6 +605,7 @@ static void ensure_arena(dino_b200_engine *e, int B, int H, int W) {
     arena_alloc(e->logits, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
     arena_alloc(e->probs, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
     arena_alloc(e->o_cls, nb * D, e->stream);
+    arena_alloc(e->ln_count, rows / GEMM_BM + 2, e->stream);   // zeroed here; every launch leaves them zero again
     DINO_CUDA(cudaStreamSynchronize(e->stream));
     e->cap_tok = ntok;
     e->cap_patch = npatch;
@@ -691,10 +715,21 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
     prof.end();
 
     // 2. encoder blocks
-    for (const Layer &ly : e->layers) {
-        prof.begin(2);
-        launch_layernorm(e->X, ly.ln1_g, ly.ln1_b, e->Xn, M, D, hp.eps, true, st);
-        prof.end();
+    // DINO_B200_FUSE_LN=1 fuses norm2 into the o-proj GEMM's epilogue and the next block's norm1 into the fc2 GEMM's
+    // (EPI_RESID_LN_F32).  Correct (bit-identical to the stand-alone kernel, tests/test_gpu_kernels.py) but OFF by default:
+    // measured on B200 it is slower (o-proj + LN 857 us fused vs 186 + 99 us apart at ViT-L, batch 64): the 8 epilogue
+    // warps of a CTA normalise a 128-row block at ~17 GB/s (latency-bound L2 read-back), and because the CTA that
+    // finishes a row block LAST does the work, it keeps landing on the CTAs that are already behind.
+    static const bool fuse_ln = [] { const char *e = getenv("DINO_B200_FUSE_LN"); return e && e[0] == '1'; }();
+    const size_t n_layers = e->layers.size();
+    for (size_t li = 0; li < n_layers; ++li) {
+        const Layer &ly = e->layers[li];
+        if (li == 0 || !fuse_ln) {
+            prof.begin(2);
+            launch_layernorm(e->X, ly.ln1_g, ly.ln1_b, e->Xn, M, D, hp.eps, true, st);
+            prof.end();
+            nl++;
+        }
         {
             GemmParams gp{};
             gp.M = M; gp.N = 3 * D; gp.K = D; gp.bias = ly.qkv.bias; gp.out = e->QKV; gp.ldo = 3 * D;
@@ -708,13 +743,17 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         {
             GemmParams gp{};
             gp.M = M; gp.N = D; gp.K = D; gp.bias = ly.proj.bias; gp.lscale = ly.ls1; gp.out = e->X; gp.ldo = D;
+            gp.ln_gamma = ly.ln2_g; gp.ln_beta = ly.ln2_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
             prof.begin(0);
-            launch_gemm(EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, tmo_x, gp, st);
+            launch_gemm(fuse_ln ? EPI_RESID_LN_F32 : EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, tmo_x, gp, st);
             prof.end();
         }
-        prof.begin(2);
-        launch_layernorm(e->X, ly.ln2_g, ly.ln2_b, e->Xn, M, D, hp.eps, true, st);
-        prof.end();
+        if (!fuse_ln) {
+            prof.begin(2);
+            launch_layernorm(e->X, ly.ln2_g, ly.ln2_b, e->Xn, M, D, hp.eps, true, st);
+            prof.end();
+            nl++;
+        }
         {
             GemmParams gp{};
             gp.M = M; gp.N = e->mlp_in; gp.K = D; gp.bias = ly.fc1.bias; gp.out = e->H1; gp.ldo = e->mlp_hidden;
@@ -725,11 +764,16 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         {
             GemmParams gp{};
             gp.M = M; gp.N = D; gp.K = e->mlp_hidden; gp.bias = ly.fc2.bias; gp.lscale = ly.ls2; gp.out = e->X; gp.ldo = D;
+            const bool fuse_next = fuse_ln && li + 1 < n_layers;     // the next block's norm1; the last block feeds the final norm
+            if (fuse_next) {
+                const Layer &nx = e->layers[li + 1];
+                gp.ln_gamma = nx.ln1_g; gp.ln_beta = nx.ln1_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
+            }
             prof.begin(0);
-            launch_gemm(EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, tmo_x, gp, st);
+            launch_gemm(fuse_next ? EPI_RESID_LN_F32 : EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, tmo_x, gp, st);
             prof.end();
         }
-        nl += 7;
+        nl += 5;
     }
 
     // 3. final LayerNorm (all tokens: the head pools over registers too) + outputs
@@ -1067,6 +1111,29 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     const uint64_t out_rows = epi == DINO_B200_EPI_PATCH_F32 ? static_cast<uint64_t>(M / (np > 0 ? np : 1)) * ntok : static_cast<uint64_t>(M);
     const CUtensorMap tmC = dino::make_tmap_out(epi, out, out_cols, out_rows, ldo);
     dino::launch_gemm(epi, BN, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
+    return DINO_B200_OK;
+    DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
+}
+
+dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const float *bias,
+                                                const float *lscale, float *X, const float *gamma, const float *beta, float eps,
+                                                void *ln_out, int *counters, void *stream) {
+    DINO_API_BEGIN
+    if (!A || !W || !X || !bias || !lscale || !gamma || !beta || !ln_out || !counters)
+        throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_gemm_resid_ln: NULL argument");
+    if (N % 128 || N > 128 * dino::LN_MAX_V4) throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED, "kernel_gemm_resid_ln: N must be a multiple of 128, at most 1536");
+    int dev = 0;
+    DINO_CUDA(cudaGetDevice(&dev));
+    if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
+    configure_kernels_once();
+    const int BN = dino::pick_bn(dino::EPI_RESID_LN_F32, N);
+    const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN / dino::gemm_cg());
+    dino::GemmParams gp{};
+    gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = X; gp.ldo = N;
+    gp.ln_gamma = gamma; gp.ln_beta = beta; gp.ln_out = static_cast<__half *>(ln_out); gp.ln_eps = eps; gp.ln_count = counters;
+    const CUtensorMap tmC = dino::make_tmap_out(dino::EPI_RESID_LN_F32, X, N, M, N);
+    dino::launch_gemm(dino::EPI_RESID_LN_F32, BN, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }

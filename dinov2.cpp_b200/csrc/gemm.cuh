@@ -24,12 +24,19 @@
 //                                                                 pre-interleaved 128 gate | 128 up per N tile
 //   EPI_PATCH_F32   X[b, 1+R+p] = acc + b + pos[1+p]              patch-embed GEMM + bias + pos-embed + token
 //                                                                 placement (dinov2.cpp:636-685)
+//   EPI_RESID_LN_F32  as RESID, plus the LayerNorm that follows the residual in the graph (norm2 after the attention
+//                   branch, the next block's norm1 after the MLP; dinov2.cpp:722-728, 694-700): every CTA counts the
+//                   column tiles it has added to each 128-row block of X; the CTA that adds the last one normalises those
+//                   rows (read back from L2, where the reduce-adds just left them) and writes the fp16 A operand of the
+//                   next GEMM.  Saves the stand-alone LayerNorm kernel's pass over X in HBM (2 x 359 MB per block at
+//                   ViT-L, batch 64) and its launch.
 #pragma once
 #include "ptx.cuh"
+#include "ln_row.cuh"
 
 namespace dino {
 
-enum : int { EPI_BIAS_F16 = 0, EPI_GELU_F16 = 1, EPI_RESID_F32 = 2, EPI_SWIGLU_F16 = 3, EPI_PATCH_F32 = 4 };
+enum : int { EPI_BIAS_F16 = 0, EPI_GELU_F16 = 1, EPI_RESID_F32 = 2, EPI_SWIGLU_F16 = 3, EPI_PATCH_F32 = 4, EPI_RESID_LN_F32 = 5 };
 
 struct GemmParams {
     int M, N, K;            // N counts weight rows (for SWIGLU: gate+up rows, output has N/2 columns)
@@ -39,6 +46,11 @@ struct GemmParams {
     int ldo;
     const float *pos;       // [1 + np, N]    (PATCH)
     int np, ntok, tok_off;  // (PATCH) patches / image, tokens / image, 1 + registers
+    // (RESID_LN) LayerNorm of the finished rows of `out`: fp16 ln_out[M, N] = LN(out row) * ln_gamma + ln_beta
+    const float *ln_gamma, *ln_beta;
+    __half *ln_out;
+    float ln_eps;
+    int *ln_count;          // one counter per 128-row block, zero on entry and zero again on exit
 };
 
 constexpr int GEMM_BM = 128;
@@ -96,6 +108,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint32_t *ln_flag = tmem_ptr + 1;                    // (RESID_LN) broadcast: this CTA completed a row block
+    constexpr bool kResid = EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN_F32;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -232,10 +246,44 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmC, stage, c0, c1);
+                if constexpr (kResid) tma_reduce_add_2d(&tmC, stage, c0, c1);
                 else tma_store_2d(&tmC, stage, c0, c1);
                 bulk_commit();
             }
+        };
+        // (RESID_LN) row block whose tile count is still to be published, and the publication itself: wait for the reduce-adds
+        // of that tile (all but the newest kResidSteps bulk groups of this warp — every warp commits exactly that many per
+        // tile, N being a multiple of BN), count the tile, and let the CTA that counted the last one normalise the rows.
+        int ln_pending = -1;
+        constexpr int kResidSteps = BN / 2 / 32;
+        auto ln_publish = [&](int blk, bool final_flush) {
+            if (lane == 0) {
+                if (final_flush) bulk_wait<0>();
+                else bulk_wait<kResidSteps>();
+            }
+            __syncwarp();
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);
+            if (threadIdx.x == 0) {
+                fence_proxy_async_all();
+                __threadfence();
+                const int done = atomicAdd(p.ln_count + blk, 1) + 1;
+                const bool last = done == num_n;
+                if (last) p.ln_count[blk] = 0;                     // ready for the next launch
+                __threadfence();
+                *ln_flag = last ? 1u : 0u;
+            }
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);
+            if (*ln_flag) {
+                const int r0 = blk * GEMM_BM + warp * (GEMM_BM / GEMM_EPI_WARPS);
+#pragma unroll 1
+                for (int rr = 0; rr < GEMM_BM / GEMM_EPI_WARPS; ++rr) {
+                    const int row = r0 + rr;
+                    if (row >= p.M) break;
+                    layernorm_row<true, true>(reinterpret_cast<const float *>(p.out) + static_cast<size_t>(row) * p.ldo, p.ln_gamma,
+                                              p.ln_beta, p.ln_out + static_cast<size_t>(row) * p.N, p.N, p.ln_eps, lane);
+                }
+            }
+            // (the flag is rewritten only after the next publication's first named barrier, which every warp reaches after this read)
         };
         int it = 0;
         for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
@@ -313,7 +361,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     stage_release(col, row0);
                 }
-            } else if constexpr (EPI == EPI_RESID_F32) {
+            } else if constexpr (kResid) {
                 constexpr int kSteps = BN / 2 / 32;                      // 32 fp32 columns (one 128-B row) per TMA reduce
 #pragma unroll 1
                 for (int c = 0; c < kSteps; ++c) {
@@ -372,6 +420,16 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));   // the leader's MMA warp waits on it
                 else mbar_arrive(&tmem_empty[as]);
             }
+            if constexpr (EPI == EPI_RESID_LN_F32) {
+                // This CTA has added one more column tile to its 128 rows of X.  The row block is published (and, if this was
+                // its last tile, normalised) one tile LATER, when its reduce-adds have certainly been performed: waiting for
+                // them right here would put an L2 round trip into every tile's epilogue.
+                if (ln_pending >= 0) ln_publish(ln_pending, false);
+                ln_pending = m_blk * CG + static_cast<int>(cta_rank);
+            }
+        }
+        if constexpr (EPI == EPI_RESID_LN_F32) {
+            if (ln_pending >= 0) ln_publish(ln_pending, true);
         }
         if (lane == 0) bulk_wait<0>();       // staging smem must outlive the last TMA store; global writes complete
     }

@@ -1,0 +1,61 @@
+// LayerNorm of one token row by one warp (reference ggml_norm, ops.cpp:3109-3158: mean, then centred variance,
+// y = (x-mean)/sqrt(var+eps); followed by *weight + bias, dinov2.cpp:694-700).  Shared by the stand-alone LayerNorm
+// kernel (elementwise.cuh) and the fused residual-GEMM epilogue (gemm.cuh) so that both produce identical bits.
+// OUT_HALF: writes the fp16 A operand of the next GEMM (the reference rounds it to fp16 inside mul_mat).
+// L2_ONLY: the row was just produced by another SM (TMA reduce-add): load with ld.global.cg, never from L1.
+#pragma once
+#include "ptx.cuh"
+
+namespace dino {
+
+constexpr int LN_MAX_V4 = 12;   // D up to 32 * 4 * 12 = 1536
+
+template <bool OUT_HALF, bool L2_ONLY>
+__device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, const float *__restrict__ gamma,
+                                              const float *__restrict__ beta, void *__restrict__ orow, int D, float eps, int lane) {
+    const int nv = D >> 2;   // float4 per row
+    const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+    float4 v[LN_MAX_V4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i] = L2_ONLY ? __ldcg(x4 + idx) : x4[idx];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / static_cast<float>(D) + eps);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+            const float y0 = (v[i].x * rstd) * g.x + b.x, y1 = (v[i].y * rstd) * g.y + b.y;
+            const float y2 = (v[i].z * rstd) * g.z + b.z, y3 = (v[i].w * rstd) * g.w + b.w;
+            if constexpr (OUT_HALF) {
+                reinterpret_cast<uint2 *>(orow)[idx] = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+            } else {
+                reinterpret_cast<float4 *>(orow)[idx] = make_float4(y0, y1, y2, y3);
+            }
+        }
+    }
+}
+
+}  // namespace dino

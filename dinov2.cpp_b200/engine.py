@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "dino_b200_get_hparams", "dino_b200_label", "dino_b200_reserve", "dino_b200_set_pos_embed",
     "dino_b200_get_pos_embed", "dino_b200_forward", "dino_b200_forward_device", "dino_b200_synchronize",
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
-    "dino_b200_kernel_gemm", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
+    "dino_b200_kernel_gemm", "dino_b200_kernel_gemm_resid_ln", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
     "dino_b200_preprocess", "dino_b200_forward_u8",
 ]
 
@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
     L.dino_b200_kernel_gemm.argtypes = [ip, vp, ip, vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, ip, ip, ip, vp]
     L.dino_b200_kernel_attention.argtypes = [vp, vp, ip, ip, ip, vp]
     L.dino_b200_kernel_layernorm.argtypes = [vp, vp, vp, vp, ip, ip, C.c_float, ip, vp]
+    L.dino_b200_kernel_gemm_resid_ln.argtypes = [vp, ip, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
     _lib = L
     return L
 
@@ -255,6 +256,12 @@ def kernel_gemm(epi: int, A: int, lda: int, W: int, ldw: int, M: int, N: int, K:
                 ldo: int, pos: int = 0, np_: int = 0, ntok: int = 0, tok_off: int = 0, stream: int = 0):
     _check(load_library().dino_b200_kernel_gemm(epi, A, lda, W, ldw, M, N, K, bias, lscale or None, out, ldo, pos or None,
                                                 np_, ntok, tok_off, stream or None))
+
+
+def kernel_gemm_resid_ln(A: int, lda: int, W: int, ldw: int, M: int, N: int, K: int, bias: int, lscale: int, X: int, gamma: int,
+                         beta: int, eps: float, ln_out: int, counters: int, stream: int = 0):
+    _check(load_library().dino_b200_kernel_gemm_resid_ln(A, lda, W, ldw, M, N, K, bias, lscale, X, gamma, beta, eps, ln_out,
+                                                         counters, stream or None))
 
 
 def kernel_attention(qkv: int, out: int, B: int, n_tok: int, D: int, stream: int = 0):

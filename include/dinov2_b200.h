@@ -174,6 +174,14 @@ enum { DINO_B200_EPI_BIAS_F16 = 0, DINO_B200_EPI_GELU_F16 = 1, DINO_B200_EPI_RES
 DINO_B200_API dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                                                      const float *bias, const float *lscale, void *out, int ldo,
                                                      const float *pos, int np, int ntok, int tok_off, void *stream);
+/* The fused residual + LayerNorm GEMM (reference dinov2.cpp:546-551 + 708-714 + 722-728):
+ * X[M,N](fp32) += lscale * (A x W^T + bias), then ln_out[M,N](fp16) = LayerNorm(X row; eps) * gamma + beta, written by
+ * whichever CTA completes a 128-row block.  counters: ceil(M/128)+1 ints, zero on entry, zero again on exit.
+ * N must be a multiple of 128 and at most 1536. */
+DINO_B200_API dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
+                                                              const float *bias, const float *lscale, float *X,
+                                                              const float *gamma, const float *beta, float eps, void *ln_out,
+                                                              int *counters, void *stream);
 /* out[B*N, D](fp16) = MHA(qkv[B*N, 3D](fp16)), head_dim 64 */
 DINO_B200_API dino_b200_status dino_b200_kernel_attention(const void *qkv, void *out, int B, int n_tok, int D, void *stream);
 /* LayerNorm rows of X[rows, D] -> fp16 (out_half != 0) or fp32 */

@@ -127,6 +127,51 @@ def test_attention(B, N, D):
     assert nmse_t(out, ref) < 5e-7
 
 
+def _attn_ref(qkv, B, N, D):
+    Hh = D // 64
+    q, k, v = [t.view(B, N, Hh, 64).permute(0, 2, 1, 3) for t in qkv.float().split(D, dim=1)]
+    return (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+
+
+@pytest.mark.parametrize("mode", ["ramp", "shuffled"])
+def test_attention_lazy_rescale_paths(mode):
+    """The running maximum only moves when a row outgrows it by more than 2^8; then O (in TMEM) and the running sum are
+    rescaled.  Random scores never do that after the first tile, so force it: scores that climb from 0 to 3000/8 along
+    the keys (growth found in every K/V tile) and the same in shuffled key order (growth at random tiles)."""
+    B, N, D = 2, 1370, 128
+    Hh = D // 64
+    g = torch.Generator(device="cuda").manual_seed(8)
+    u = torch.nn.functional.normalize(torch.randn(B, Hh, 1, 64, device="cuda", generator=g), dim=-1)
+    amp = torch.linspace(0.0, 3000.0, N, device="cuda")
+    if mode == "shuffled":
+        amp = amp[torch.randperm(N, device="cuda", generator=g)]
+    k = u * (amp.view(1, 1, N, 1) / 8.0) + 0.3 * torch.randn(B, Hh, N, 64, device="cuda", generator=g)
+    q = 8.0 * u + 0.3 * torch.randn(B, Hh, N, 64, device="cuda", generator=g)
+    v = torch.randn(B, Hh, N, 64, device="cuda", generator=g)
+    qkv = torch.cat([x.permute(0, 2, 1, 3).reshape(B * N, D) for x in (q, k, v)], dim=1).half().contiguous()
+    out = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.half)
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, _attn_ref(qkv, B, N, D)) < 5e-7
+
+
+def test_attention_persistent_many_items_per_cta():
+    """ViT-L bench shape: 6144 (image, head, query block) items over 148 persistent CTAs, ~41 per CTA, every sixth one with
+    a single query tile — the barrier phases, the TMEM ring and the K/V ring must survive item boundaries."""
+    B, N, D = 64, 1370, 1024
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).half()
+    out = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.half)
+    for _ in range(2):
+        E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    for img in (0, 31, B - 1):
+        ref = _attn_ref(qkv[img * N:(img + 1) * N], 1, N, D)
+        assert nmse_t(out[img * N:(img + 1) * N], ref) < 5e-7
+
+
 def test_attention_large_logits_do_not_overflow():
     """Online softmax must survive |s| far outside fp16's exp range (real checkpoints have outlier activations)."""
     B, N, D = 1, 300, 64
@@ -157,3 +202,33 @@ def test_layernorm(rows, D):
     torch.cuda.synchronize()
     assert nmse_t(o32, ref) < 1e-12
     assert nmse_t(o16, ref) < 2e-7
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 384, 384), (2740, 1024, 1024), (5000, 1024, 4096), (999, 1536, 256)])
+def test_gemm_residual_with_fused_layernorm(M, N, K):
+    """EPI_RESID_LN: X += ls * (A W^T + b) exactly as EPI_RESID, and the CTA that completes a 128-row block writes
+    fp16 LayerNorm(X) * gamma + beta for it (dinov2.cpp:708-714 + 722-728); counters return to zero."""
+    A, W, bias, ref = _operands(M, N, K, seed=10)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ls = torch.rand(N, device="cuda", generator=g) + 0.3
+    gam = torch.randn(N, device="cuda", generator=g)
+    bet = torch.randn(N, device="cuda", generator=g)
+    X0 = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.5
+    cnt = torch.zeros((M + 127) // 128 + 1, device="cuda", dtype=torch.int32)
+    for rep in range(2):                                    # second launch: the counters must have been left at zero
+        X = X0.clone()
+        ln = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+        E.kernel_gemm_resid_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), X.data_ptr(),
+                               gam.data_ptr(), bet.data_ptr(), 1e-6, ln.data_ptr(), cnt.data_ptr())
+        torch.cuda.synchronize()
+        want = X0 + ls * ref
+        assert nmse_t(X, want) < 1e-11
+        assert int(cnt.abs().sum()) == 0
+        # bit-identical to the stand-alone LayerNorm kernel on the same X
+        o16 = torch.empty(M, N, device="cuda", dtype=torch.half)
+        E.kernel_layernorm(X.data_ptr(), gam.data_ptr(), bet.data_ptr(), o16.data_ptr(), M, N, 1e-6, True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(ln).all()
+        assert torch.equal(ln, o16)
+        lref = torch.nn.functional.layer_norm(X.double(), (N,), gam.double(), bet.double(), 1e-6)
+        assert nmse_t(ln, lref) < 2e-7

@@ -37,3 +37,24 @@ for name, epi, N, K in shapes:
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / iters
     print(f"gemm {name:5s} M={M} N={N} K={K}: {ms*1000:7.1f} us  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s   [{tag}]", flush=True)
+    if f32:
+        # the same GEMM with the following LayerNorm fused into its epilogue, and the stand-alone LayerNorm it replaces
+        gam = torch.randn(N, device="cuda"); bet = torch.randn(N, device="cuda")
+        ln = torch.empty(M, N, device="cuda", dtype=torch.half)
+        cnt = torch.zeros((M + 127) // 128 + 1, device="cuda", dtype=torch.int32)
+        def run2():
+            E.kernel_gemm_resid_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), out.data_ptr(),
+                                   gam.data_ptr(), bet.data_ptr(), 1e-6, ln.data_ptr(), cnt.data_ptr())
+        def run3():
+            E.kernel_layernorm(out.data_ptr(), gam.data_ptr(), bet.data_ptr(), ln.data_ptr(), M, N, 1e-6, True)
+        for fn, nm in ((run2, name + "+ln"), (run3, "ln")):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            print(f"gemm {nm:7s} M={M} N={N} K={K}: {ms*1000:7.1f} us   [{tag}]", flush=True)
