@@ -371,6 +371,12 @@ struct dino_b200_engine {
     // host-API output staging in device memory
     float *o_cls = nullptr, *o_patch = nullptr;
     size_t cap_o_patch = 0;
+    // pipelined host interface (dino_b200_submit / dino_b200_wait): two input slots, uploads on their own stream
+    cudaStream_t copy_stream = nullptr;
+    float *d_in[2] = {nullptr, nullptr};
+    size_t cap_in[2] = {0, 0};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint64_t n_submitted = 0, n_waited = 0;
     int *ln_count = nullptr;          // per-128-row-block tile counters of the fused residual-GEMM + LayerNorm epilogue
     uint8_t *d_u8 = nullptr;          // raw frames for on-device preprocessing
     size_t cap_u8 = 0;
@@ -954,6 +960,12 @@ void dino_b200_destroy(dino_b200_engine *e) {
     dino::free_arena(e);
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_u8) cudaFree(e->d_u8);
+    for (int i = 0; i < 2; ++i) {
+        if (e->d_in[i]) cudaFree(e->d_in[i]);
+        if (e->ev_up[i]) cudaEventDestroy(e->ev_up[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (auto &pe : e->prof) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto &pe : e->prof_pool) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -1047,6 +1059,78 @@ dino_b200_status dino_b200_forward(dino_b200_engine *e, const float *images, int
     if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs, e->probs, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
     DINO_CUDA(cudaStreamSynchronize(st));
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+// Pipelined host interface.  Slot k % 2 of batch k: upload on the copy stream (may run under the forward pass of batch
+// k-1), then forward + read-back on the engine stream.  At most two batches in flight.
+dino_b200_status dino_b200_submit(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
+                                  float *patch, float *logits, float *probs) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit: bad batch or image size");
+    if (e->n_submitted - e->n_waited >= 2) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit: two batches already in flight; call dino_b200_wait first");
+    DINO_CUDA(cudaSetDevice(e->device));
+    const int slot = static_cast<int>(e->n_submitted & 1);
+    if (!e->copy_stream) {
+        DINO_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_up[i], cudaEventDisableTiming));
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
+    const size_t np = static_cast<size_t>(H / ps) * (W / ps);
+    const size_t n_in = static_cast<size_t>(B) * 3 * H * W;
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    // anything that (re)allocates waits for the work in flight first
+    const bool grow = n_in > e->cap_in[slot] || (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch);
+    if (grow) {
+        DINO_CUDA(cudaStreamSynchronize(e->copy_stream));
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        if (n_in > e->cap_in[slot]) {
+            if (e->d_in[slot]) DINO_CUDA(cudaFree(e->d_in[slot]));
+            e->d_in[slot] = nullptr;
+            e->cap_in[slot] = 0;
+            DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->d_in[slot]), n_in * sizeof(float)));
+            e->cap_in[slot] = n_in;
+        }
+        if (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch) {
+            if (e->o_patch) DINO_CUDA(cudaFree(e->o_patch));
+            e->o_patch = nullptr;
+            e->cap_o_patch = 0;
+            DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->o_patch), static_cast<size_t>(B) * np * D * sizeof(float)));
+            e->cap_o_patch = static_cast<size_t>(B) * np * D;
+        }
+    }
+    dino::ensure_arena(e, B, H, W);     // synchronises the engine stream itself when it has to grow
+    cudaStream_t st = e->stream;
+    // the slot's previous forward pass (batch k-2) has been waited for by the caller or is ordered before us on `st`;
+    // the upload must not overwrite the slot while that forward still reads it
+    if (e->n_submitted >= 2) DINO_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+    DINO_CUDA(cudaMemcpyAsync(e->d_in[slot], images, n_in * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    DINO_CUDA(cudaEventRecord(e->ev_up[slot], e->copy_stream));
+    DINO_CUDA(cudaStreamWaitEvent(st, e->ev_up[slot], 0));
+    dino::forward_device(e, e->d_in[slot], layout, B, H, W, flags, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
+                         (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
+    if (cls) DINO_CUDA(cudaMemcpyAsync(cls, e->o_cls, static_cast<size_t>(B) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (patch) DINO_CUDA(cudaMemcpyAsync(patch, e->o_patch, static_cast<size_t>(B) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs, e->probs, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DINO_CUDA(cudaEventRecord(e->ev_done[slot], st));
+    e->n_submitted++;
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_wait(dino_b200_engine *e) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (e->n_waited >= e->n_submitted) throw dino::StatusError(DINO_B200_ERR_INVALID, "wait: nothing in flight");
+    DINO_CUDA(cudaSetDevice(e->device));
+    DINO_CUDA(cudaEventSynchronize(e->ev_done[e->n_waited & 1]));
+    e->n_waited++;
     return DINO_B200_OK;
     DINO_API_END(e)
 }

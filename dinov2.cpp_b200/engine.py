@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "dino_b200_get_pos_embed", "dino_b200_forward", "dino_b200_forward_device", "dino_b200_synchronize",
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
     "dino_b200_kernel_gemm", "dino_b200_kernel_gemm_resid_ln", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
-    "dino_b200_preprocess", "dino_b200_forward_u8",
+    "dino_b200_preprocess", "dino_b200_forward_u8", "dino_b200_submit", "dino_b200_wait",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library() -> C.CDLL:
     L.dino_b200_synchronize.argtypes = [vp]
     L.dino_b200_preprocess.argtypes = [vp, vp, ip, ip, ip, ip, fp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.dino_b200_forward_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp]
+    L.dino_b200_submit.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
+    L.dino_b200_wait.argtypes = [vp]
     L.dino_b200_last_error.argtypes = [vp]
     L.dino_b200_last_error.restype = C.c_char_p
     L.dino_b200_kernel_launches.argtypes = [vp]
@@ -202,6 +204,26 @@ class Engine:
             _host_ptr(res.get("cls")), _host_ptr(res.get("patch_tokens")),
             _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))), self._h)
         return res
+
+    def submit(self, images: np.ndarray, out: Dict[str, np.ndarray], classify: bool = False, layout: int = LAYOUT_BGR_HWC):
+        """Pipelined forward: enqueue upload + forward + read-back of one batch and return at once (at most two in flight).
+        `images` (float32, C-contiguous) and the arrays in `out` ("cls", "patch_tokens", "logits", "probs" — whichever are
+        wanted) must stay alive, and should be pinned, until the matching wait() returns."""
+        if images.dtype != np.float32 or not images.flags["C_CONTIGUOUS"] or images.ndim != 4:
+            raise ValueError("submit needs a C-contiguous float32 4-D array (no hidden copy may be made)")
+        if layout == LAYOUT_BGR_HWC:
+            B, H, W, ch = images.shape
+        else:
+            B, ch, H, W = images.shape
+        if ch != 3:
+            raise ValueError("images must have 3 channels")
+        _check(load_library().dino_b200_submit(
+            self._h, images.ctypes.data, layout, B, H, W, FLAG_CLASSIFY if classify else 0, _host_ptr(out.get("cls")),
+            _host_ptr(out.get("patch_tokens")), _host_ptr(out.get("logits")), _host_ptr(out.get("probs"))), self._h)
+
+    def wait(self):
+        """Block until the oldest submitted batch has completed."""
+        _check(load_library().dino_b200_wait(self._h), self._h)
 
     def preprocess_size(self, H: int, W: int, classify: bool):
         """Output size of the reference's preprocessing for an H x W frame (dinov2.cpp:111-116, 140-141)."""

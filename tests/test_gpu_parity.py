@@ -182,3 +182,26 @@ def test_full_size_properties_vitl14(workdir):
     bet = gguf_io.to_numpy(gg.tensors["layernorm.bias"])
     z = (a["patch_tokens"][0] - bet) / gam
     assert np.abs(z.mean(axis=1)).max() < 1e-3 and np.abs(z.var(axis=1) - 1).max() < 1e-2
+
+
+def test_pipelined_submit_wait_matches_synchronous_forward(workdir):
+    """dino_b200_submit / dino_b200_wait (two batches in flight, uploads under the previous forward) return exactly what
+    the synchronous dino_b200_forward returns for each batch, in order."""
+    import torch
+    path = os.path.join(workdir, "tiny_pipe.gguf")
+    cfg = synth.CONFIGS["tiny"]
+    synth.write_synth_gguf(path, cfg, seed=3)
+    batches = [torch.from_numpy(synth.lcg_batch(10 * k, 3, 70, 70)).pin_memory().numpy() for k in range(5)]
+    with d.Engine(path) as eng:
+        want = [eng.forward(b, classify=True) for b in batches]
+        outs = [{k: np.empty_like(v) for k, v in want[0].items()} for _ in range(len(batches))]
+        eng.submit(batches[0], outs[0], classify=True)
+        for k in range(1, len(batches)):
+            eng.submit(batches[k], outs[k], classify=True)
+            eng.wait()
+        eng.wait()
+        with pytest.raises(d.DinoB200Error):
+            eng.wait()                                   # nothing in flight
+        for k in range(len(batches)):
+            for name in want[k]:
+                assert np.array_equal(outs[k][name], want[k][name]), (k, name)
