@@ -44,6 +44,19 @@ def flops_per_image(cfg, n_tok: int) -> dict:
     return {"linear": float(linear), "attention": float(attn), "total": float(linear + attn)}
 
 
+def load_gemm_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu --set full capture (profiles/r01_gemm_traffic.json), ViT-L b64 only."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return {"bytes_per_launch": d["dram_bytes_per_launch_mean"],
+                "algorithmic_bytes_per_launch": sum(k["algorithmic_bytes"] for k in d["kernels"]) / len(d["kernels"]),
+                "source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the qkv / o-proj / fc1 / fc2 launches of one block)"}
+    except Exception:
+        return None
+
+
 def load_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -95,14 +108,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ensure_gguf(name: str, rank: int, barrier) -> str:
+def ensure_gguf(name: str, rank: int, barrier, quant=None) -> str:
     from dinov2_b200 import synth
     d = os.environ.get("DINO_BENCH_DIR", "/tmp/dino_bench")
     os.makedirs(d, exist_ok=True)
-    path = os.path.join(d, f"{name}_f16_seed0.gguf")
+    path = os.path.join(d, f"{name}_{quant or 'f16'}_seed0.gguf")
     if rank == 0 and not os.path.exists(path):
         tmp = path + f".tmp{os.getpid()}"
-        synth.write_synth_gguf(tmp, synth.CONFIGS[name], seed=0)
+        synth.write_synth_gguf(tmp, synth.CONFIGS[name], seed=0, quant=quant)
         os.replace(tmp, path)
     barrier()
     return path
@@ -140,6 +153,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--features", action="store_true", help="feature-extraction mode (patch tokens) instead of classify")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quant", default=None, choices=[None, "q8_0"], help="checkpoint weight format (q8_0: BASELINE configs[4])")
     ap.add_argument("--gather", default="none", choices=["none", "cls", "patch"],
                     help="all-gather the per-image features across ranks inside the timed step (NCCL over NVLink)")
     args = ap.parse_args()
@@ -153,13 +167,14 @@ def main():
     from dinov2_b200 import synth
     cfg = synth.CONFIGS[args.model]
     n_tok = 1 + cfg.num_register_tokens + (H // cfg.patch_size) * (W // cfg.patch_size)
-    workload = f"{args.model} 518x518 fp16-operand/fp32-accumulate forward, batch {args.batch}/GPU, {'classify' if classify else 'features'}"
+    workload = (f"{args.model} {args.quant or 'f16'} checkpoint, 518x518 fp16-operand/fp32-accumulate forward, batch {args.batch}/GPU, "
+                f"{'classify' if classify else 'features'}")
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        path = ensure_gguf(args.model, 0, lambda: None)
+        path = ensure_gguf(args.model, 0, lambda: None, args.quant)
         steps = max(1, args.steps)
         cb = time_reference(path, steps, max(0, min(args.warmup, 1)), classify)
         line = {"impl": "reference", "metric": "images/sec " + args.model + " 518px forward", "value": cb["value"], "unit": "images/s",
@@ -191,7 +206,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    path = ensure_gguf(args.model, rank, barrier)
+    path = ensure_gguf(args.model, rank, barrier, args.quant)
     eng = d.Engine(path, device=local_rank)
     B = args.batch
     eng.reserve(B, H, W)
@@ -308,6 +323,7 @@ def main():
         e2e_value = total_images / (e2e_ms / 1e3)
         ms_per_step = elapsed_ms / args.steps
         gemm_launches_per_step = 1 + 4 * cfg.num_hidden_layers
+        traffic = load_gemm_traffic() if (args.model == "vitl14" and B == 64) else None
         gemm_tflops = fl["linear"] * B / (last_prof["gemm_ms"] / 1e3) / 1e12 if last_prof["gemm_ms"] > 0 else 0.0
         attn_tflops = fl["attention"] * B / (last_prof["attn_ms"] / 1e3) / 1e12 if last_prof["attn_ms"] > 0 else 0.0
         step_tflops = fl["total"] * B / (ms_per_step / 1e3) / 1e12
@@ -331,7 +347,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tcgen05 (all weight GEMMs, %d launches/step)" % gemm_launches_per_step,
                          "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["sustained"], "peak_kind": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
-                         "traffic": None,
+                         "traffic": (traffic["bytes_per_launch"] if traffic else None), "traffic_detail": traffic,
                          "attention_tflops": attn_tflops, "whole_step_tflops": step_tflops,
                          "whole_step_frac_of_burst": step_tflops / peaks["burst"],
                          "ms_last_step": last_prof},

@@ -54,9 +54,9 @@ __device__ __forceinline__ float exp2_poly3_v7(float x) {
 }
 
 // Rare path of the lazy running-max correction: scale this thread's row of O_t (64 fp32 columns) in TMEM and, when the
-// growth was found in the middle of a tile, the 32 packed columns of P (keys 0-63) it has already written.  Inlined and
+// growth was found in the middle of a tile, the first p_cols packed columns of P it has already written.  Inlined and
 // rolled (8 columns at a time): a call here would make ptxas save the 64-128 live score registers on EVERY tile.
-__device__ __forceinline__ void attn7_rescale(uint32_t o_addr, uint32_t p_addr, float alpha, bool do_o, bool do_p) {
+__device__ __forceinline__ void attn7_rescale(uint32_t o_addr, uint32_t p_addr, float alpha, bool do_o, int p_cols) {
     tmem_st_wait();                                       // this thread's earlier P stores have landed
     if (do_o) {
 #pragma unroll 1
@@ -69,10 +69,10 @@ __device__ __forceinline__ void attn7_rescale(uint32_t o_addr, uint32_t p_addr, 
             tmem_st_32x32b_x8(o_addr + i, a);
         }
     }
-    if (do_p) {
+    if (p_cols > 0) {
         const __half2 a2 = __float2half2_rn(alpha);
 #pragma unroll 1
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < p_cols; i += 8) {
             uint32_t q[8];
             tmem_ld_32x32b_x8(p_addr + i, q);
             tmem_ld_wait();
@@ -391,7 +391,7 @@ attention_fwd_v7(const __grid_constant__ CUtensorMap tmQKV, const Attn7Params p)
                         const float alpha = grow ? ex2_approx((m_used - mx01) * c) : 1.0f;
                         if (grow) m_used = mx01;
                         l_run *= alpha;
-                        attn7_rescale(o_addr, lo, alpha, true, false);
+                        attn7_rescale(o_addr, lo, alpha, true, 0);
                     }
                 }
                 // B. chunks 2,3 start loading (S(n) is complete: chunks 0,1 came out of it)
@@ -431,7 +431,7 @@ attention_fwd_v7(const __grid_constant__ CUtensorMap tmQKV, const Attn7Params p)
                         l_run *= alpha;
                         ls[0] *= alpha;
                         ls[1] *= alpha;
-                        attn7_rescale(o_addr, lo, alpha, j > 0, true);
+                        attn7_rescale(o_addr, lo, alpha, j > 0, 32);
                     }
                 }
                 // F. chunk 2

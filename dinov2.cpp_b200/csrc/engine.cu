@@ -12,6 +12,7 @@
 #include "attention5.cuh"
 #include "attention6.cuh"
 #include "attention7.cuh"
+#include "attention8.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -137,6 +138,7 @@ static void configure_kernels_once() {
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, AT6_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
+            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM_BYTES));
         } catch (const std::exception &e) {
             err = e.what();
         }
@@ -193,12 +195,13 @@ static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorM
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=1|2|3|4|6 selects another generation of the attention kernel for A/B comparisons (default: 5;
-// 6 = the 16-softmax-warp experiment, measured slower: 872 vs 828 us per ViT-L layer at batch 64).
+// DINO_B200_ATTN=1..7 selects another generation of the attention kernel for A/B comparisons (default: 8 = v5's TMEM ring
+// with intra-tile pipelining).  Per ViT-L layer at batch 64 on B200: v3 932 us, v4 885, v5 780, v6 (16 softmax warps) 872,
+// v7 (loads pipelined across tiles) 878, v8 768.
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 5;
+        return (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 8;
     }();
     return v;
 }
@@ -235,6 +238,21 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
         ap.scale_log2 = scale_log2;
         const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
         attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
+    } else if (attention_variant() == 8) {
+        Attn8Params ap;
+        ap.n_tok = n_tok;
+        ap.hidden = D;
+        ap.n_heads = D / ATT_HD;
+        ap.n_qblk = (n_tok + 255) / 256;
+        ap.num_items = B * ap.n_heads * ap.n_qblk;
+        ap.out = out;
+        ap.scale_log2 = scale_log2;
+        ap.trace = nullptr;
+#ifdef AT8_TRACE
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        attention_fwd_v8<<<grid, AT8_THREADS, AT8_SMEM_BYTES, st>>>(tmQKV, ap);
     } else if (attention_variant() == 7) {
         Attn7Params ap;
         ap.n_tok = n_tok;

@@ -71,7 +71,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 if os.path.exists(os.path.join(G, f"{tag}_launches_bench.csv")):
     launches(os.path.join(G, f"{tag}_launches_bench.csv"), os.path.join(P, f"{tag}_launches_bench.md"), "9 forward passes + weight upload")
-for name, title in (("gemm", "GEMM kernels (gemm_f16_tcgen05)"), ("attn", "Attention kernel (attention_fwd_v3)")):
+for name, title in (("gemm", "GEMM kernels (gemm_f16_tcgen05)"), ("attn", "Attention kernel (attention_fwd_v8)")):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if os.path.exists(rep):
         raw_metrics(rep, os.path.join(P, f"{tag}_ncu_{name}.md"), title, WANT)
