@@ -147,20 +147,53 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restri
 
 // ---------------------------------------------------------------------------------------------
 // Load-time weight preparation.
-// q8_0 -> fp16: blocks of {half d; int8 q[32]} along K (reference ggml-common.h:209-213,
-// dequantize_row_q8_0 in ggml-quants.c).  One thread per block; `row_map` (optional) permutes output rows
-// (used to interleave SwiGLU gate/up rows per N tile).
-__global__ void dequant_q8_0_kernel(const uint8_t *__restrict__ raw, __half *__restrict__ W, long long n_blocks,
-                                    int blocks_per_row, int ld_out, const int *__restrict__ row_map) {
+// Quantised weights -> fp16, once at load.  Blocks of 32 elements along K in the reference's layouts (ggml-common.h:170-213,
+// dequantize_row_q4_0 .. q8_0 in ggml-quants.c:255-353):
+//   q8_0 {half d; int8 q[32]}                    x = q d
+//   q4_0 {half d; u8 qs[16]}                     x[j] = ((qs[j] & 15) - 8) d,  x[j+16] = ((qs[j] >> 4) - 8) d
+//   q4_1 {half d, m; u8 qs[16]}                  x = q d + m
+//   q5_0 {half d; u32 qh; u8 qs[16]}             fifth bit of element j = bit j of qh;  x = (q - 16) d
+//   q5_1 {half d, m; u32 qh; u8 qs[16]}          x = q d + m
+// computed in fp32 exactly as the reference does, then rounded once to fp16 (the GEMM operand type).  One thread per
+// block; `row_map` (optional) permutes output rows (used to interleave SwiGLU gate/up rows per N tile).
+__device__ __forceinline__ float dq_half_at(const uint8_t *p) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(p[0] | (p[1] << 8))));
+}
+template <int TYPE>
+__global__ void dequant_kernel(const uint8_t *__restrict__ raw, __half *__restrict__ W, long long n_blocks, int blocks_per_row,
+                               int ld_out, const int *__restrict__ row_map) {
+    constexpr int kBytes = TYPE == 2 ? 18 : TYPE == 3 ? 20 : TYPE == 6 ? 22 : TYPE == 7 ? 24 : 34;
+    constexpr bool kHasMin = TYPE == 3 || TYPE == 7;
+    constexpr bool kFive = TYPE == 6 || TYPE == 7;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_blocks;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint8_t *blk = raw + i * 34;
-        const float d = __half2float(__ushort_as_half(static_cast<unsigned short>(blk[0] | (blk[1] << 8))));
+        const uint8_t *blk = raw + i * kBytes;
+        const float d = dq_half_at(blk);
         const long long row = i / blocks_per_row;
         const int kb = static_cast<int>(i % blocks_per_row);
         const long long orow = row_map ? row_map[row] : row;
         __half *dst = W + orow * ld_out + kb * 32;
-        for (int j = 0; j < 32; ++j) dst[j] = __float2half_rn(d * static_cast<float>(static_cast<int8_t>(blk[2 + j])));
+        if constexpr (TYPE == 8) {
+            for (int j = 0; j < 32; ++j) dst[j] = __float2half_rn(d * static_cast<float>(static_cast<int8_t>(blk[2 + j])));
+        } else {
+            const float m = kHasMin ? dq_half_at(blk + 2) : 0.f;
+            const uint8_t *q = blk + (kHasMin ? 4 : 2);
+            uint32_t qh = 0;
+            if constexpr (kFive) {
+                qh = q[0] | (q[1] << 8) | (q[2] << 16) | (static_cast<uint32_t>(q[3]) << 24);
+                q += 4;
+            }
+            constexpr int kBias = kHasMin ? 0 : (kFive ? 16 : 8);
+            for (int j = 0; j < 16; ++j) {
+                int x0 = q[j] & 0x0F, x1 = q[j] >> 4;
+                if constexpr (kFive) {
+                    x0 |= ((qh >> j) << 4) & 0x10;
+                    x1 |= (qh >> (j + 12)) & 0x10;
+                }
+                dst[j] = __float2half_rn(static_cast<float>(x0 - kBias) * d + m);
+                dst[j + 16] = __float2half_rn(static_cast<float>(x1 - kBias) * d + m);
+            }
+        }
     }
 }
 

@@ -489,12 +489,20 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
             DINO_CUDA(cudaStreamSynchronize(e->stream));
             DINO_CUDA(cudaFree(tmp));
         }
-    } else if (w.type == DINO_B200_TYPE_Q8_0) {
-        if (K % 32 || L.ldw != K) throw StatusError(DINO_B200_ERR_FORMAT, std::string("q8_0 tensor '") + w.name + "' has an unsupported row length");
+    } else if (w.type == DINO_B200_TYPE_Q8_0 || w.type == DINO_B200_TYPE_Q4_0 || w.type == DINO_B200_TYPE_Q4_1 ||
+               w.type == DINO_B200_TYPE_Q5_0 || w.type == DINO_B200_TYPE_Q5_1) {
+        if (K % 32 || L.ldw != K) throw StatusError(DINO_B200_ERR_FORMAT, std::string("quantised tensor '") + w.name + "' has an unsupported row length");
         uint8_t *raw = nullptr;
         DINO_CUDA(cudaMalloc(&raw, w.nbytes));
         h2d(e, raw, w.data, w.nbytes);
-        dequant_q8_0_kernel<<<grid, 256, 0, e->stream>>>(raw, L.w, static_cast<long long>(N) * (K / 32), K / 32, L.ldw, d_perm);
+        const long long nblk = static_cast<long long>(N) * (K / 32);
+        switch (w.type) {
+            case DINO_B200_TYPE_Q4_0: dequant_kernel<2><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q4_1: dequant_kernel<3><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q5_0: dequant_kernel<6><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q5_1: dequant_kernel<7><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            default: dequant_kernel<8><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+        }
         DINO_CUDA(cudaGetLastError());
         DINO_CUDA(cudaStreamSynchronize(e->stream));
         DINO_CUDA(cudaFree(raw));

@@ -61,11 +61,13 @@ inline uint64_t type_row_bytes(int32_t type, int64_t ne0) {
     switch (type) {
         case 0: return static_cast<uint64_t>(ne0) * 4;          // F32
         case 1: return static_cast<uint64_t>(ne0) * 2;          // F16
-        case 8:                                                  // Q8_0: 34-byte blocks of 32
-            if (ne0 % 32) throw std::runtime_error("gguf: q8_0 row not a multiple of 32");
-            return static_cast<uint64_t>(ne0) / 32 * 34;
+        case 2: case 3: case 6: case 7: case 8: {                // Q4_0 / Q4_1 / Q5_0 / Q5_1 / Q8_0: blocks of 32 elements
+            static const int kBlockBytes[9] = {0, 0, 18, 20, 0, 0, 22, 24, 34};
+            if (ne0 % 32) throw std::runtime_error("gguf: quantised row not a multiple of 32");
+            return static_cast<uint64_t>(ne0) / 32 * kBlockBytes[type];
+        }
         default: throw std::runtime_error("gguf: unsupported tensor type " + std::to_string(type) +
-                                          " (engine handles F32, F16, Q8_0)");
+                                          " (engine handles F32, F16, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0)");
     }
 }
 }  // namespace gguf_detail

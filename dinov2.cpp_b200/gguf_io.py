@@ -33,9 +33,16 @@ DEFAULT_ALIGNMENT = 32
 # ggml_type ids (reference ggml/include/ggml.h enum ggml_type)
 GGML_TYPE_F32 = 0
 GGML_TYPE_F16 = 1
+GGML_TYPE_Q4_0 = 2
+GGML_TYPE_Q4_1 = 3
+GGML_TYPE_Q5_0 = 6
+GGML_TYPE_Q5_1 = 7
 GGML_TYPE_Q8_0 = 8
 QK8_0 = 32
 Q8_0_BLOCK_BYTES = 34  # half d + 32 x int8
+# bytes per 32-element block of the legacy ggml quant types (reference ggml-common.h:170-213):
+#   q4_0 {half d; u8 qs[16]}  q4_1 {half d, m; u8 qs[16]}  q5_0 {half d; u8 qh[4]; u8 qs[16]}  q5_1 {half d, m; u8 qh[4]; u8 qs[16]}
+QUANT_BLOCK_BYTES = {GGML_TYPE_Q4_0: 18, GGML_TYPE_Q4_1: 20, GGML_TYPE_Q5_0: 22, GGML_TYPE_Q5_1: 24, GGML_TYPE_Q8_0: 34}
 
 # gguf value types (reference ggml/include/gguf.h enum gguf_type)
 T_U8, T_I8, T_U16, T_I16, T_U32, T_I32, T_F32, T_BOOL, T_STR, T_ARR, T_U64, T_I64, T_F64 = range(13)
@@ -73,9 +80,9 @@ def tensor_nbytes(ggml_type: int, ne) -> int:
         return n * 4
     if ggml_type == GGML_TYPE_F16:
         return n * 2
-    if ggml_type == GGML_TYPE_Q8_0:
-        assert ne[0] % QK8_0 == 0, "q8_0 rows must be a multiple of 32"
-        return n // QK8_0 * Q8_0_BLOCK_BYTES
+    if ggml_type in QUANT_BLOCK_BYTES:
+        assert ne[0] % QK8_0 == 0, "quantised rows must be a multiple of 32"
+        return n // QK8_0 * QUANT_BLOCK_BYTES[ggml_type]
     raise ValueError(f"unsupported ggml type {ggml_type}")
 
 
@@ -235,6 +242,44 @@ def dequantize_q8_0(raw: np.ndarray, ne) -> np.ndarray:
     return (q * d).reshape(tuple(reversed(ne)))
 
 
+def dequantize_legacy(raw: np.ndarray, ne, ggml_type: int, split: bool = False):
+    """raw q4_0 / q4_1 / q5_0 / q5_1 bytes -> float32 in numpy order, restating dequantize_row_q4_0 .. q5_1 (reference
+    ggml-quants.c:255-339): element j < 16 of a block comes from the low nibble of qs[j], element j + 16 from the high
+    nibble; q5 adds bit j (resp. j + 16) of the 32-bit qh as the fifth bit; q*_0: (q - 8 | 16) * d, q*_1: q * d + m.
+    split=True returns (q * d, m per block) instead, which the oracle needs for the q8_1 dot product."""
+    k = ne[0]
+    rows = 1
+    for d in ne[1:]:
+        rows *= d
+    bb = QUANT_BLOCK_BYTES[ggml_type]
+    b = raw.reshape(rows, k // 32, bb)
+    d = b[..., 0:2].copy().view(np.float16).astype(np.float32)                     # [rows, nb, 1]
+    off = 2
+    m = None
+    if ggml_type in (GGML_TYPE_Q4_1, GGML_TYPE_Q5_1):
+        m = b[..., 2:4].copy().view(np.float16).astype(np.float32)
+        off = 4
+    hi_bits = None
+    if ggml_type in (GGML_TYPE_Q5_0, GGML_TYPE_Q5_1):
+        qh = b[..., off:off + 4].copy().view(np.uint32)                            # [rows, nb, 1]
+        j = np.arange(32, dtype=np.uint32)
+        hi_bits = ((qh >> j) & 1).astype(np.int32) << 4                            # bit j -> element j (j < 16: low half)
+        off += 4
+    qs = b[..., off:off + 16]
+    q = np.concatenate([qs & 0x0F, qs >> 4], axis=-1).astype(np.int32)              # elements 0..15, 16..31
+    if hi_bits is not None:
+        q = q | hi_bits
+    if ggml_type == GGML_TYPE_Q4_0:
+        q = q - 8
+    elif ggml_type == GGML_TYPE_Q5_0:
+        q = q - 16
+    qd = q.astype(np.float32) * d
+    shape = tuple(reversed(ne))
+    if split:
+        return qd.reshape(shape), (m if m is not None else np.zeros_like(d)).reshape(rows, k // 32)
+    return (qd + m if m is not None else qd).astype(np.float32).reshape(shape)
+
+
 def to_numpy(t: GGUFTensor) -> np.ndarray:
     """Decode to float32 (F32/Q8_0) or float16 (F16), numpy order (reverse of ggml ne)."""
     shape = tuple(reversed(t.ne))
@@ -244,4 +289,6 @@ def to_numpy(t: GGUFTensor) -> np.ndarray:
         return t.data.view(np.float16).reshape(shape)
     if t.ggml_type == GGML_TYPE_Q8_0:
         return dequantize_q8_0(t.data, t.ne)
+    if t.ggml_type in QUANT_BLOCK_BYTES:
+        return dequantize_legacy(t.data, t.ne, t.ggml_type)
     raise ValueError(t.ggml_type)

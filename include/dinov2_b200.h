@@ -54,7 +54,8 @@ typedef struct {
 } dino_b200_hparams;
 
 /* ggml_type ids accepted for weights (reference ggml.h enum ggml_type). */
-enum { DINO_B200_TYPE_F32 = 0, DINO_B200_TYPE_F16 = 1, DINO_B200_TYPE_Q8_0 = 8 };
+enum { DINO_B200_TYPE_F32 = 0, DINO_B200_TYPE_F16 = 1, DINO_B200_TYPE_Q4_0 = 2, DINO_B200_TYPE_Q4_1 = 3, DINO_B200_TYPE_Q5_0 = 6,
+       DINO_B200_TYPE_Q5_1 = 7, DINO_B200_TYPE_Q8_0 = 8 };   /* = ggml_type; the five quantised types of the reference's quantize tool */
 
 /* One checkpoint tensor as the reference holds it in dino_model::tensors (dinov2.h:54): ggml `ne`
  * (fastest dimension first) and a host pointer to the raw bytes. */

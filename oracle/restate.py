@@ -66,6 +66,20 @@ def q8_roundtrip(x: np.ndarray) -> np.ndarray:
     return (q * r16(d)[..., None]).astype(f32).reshape(m, k)
 
 
+def q8_1_quantise(x: np.ndarray):
+    """quantize_row_q8_1 (ggml-quants.c:220-253): as q8_0 plus s = fp16(d * sum(q)) per block, d being the unrounded scale.
+    Returns (dequantised activations q * fp16(d), s) with s of shape [m, k/32]."""
+    m, k = x.shape
+    blk = x.reshape(m, k // 32, 32)
+    amax = np.abs(blk).max(axis=2)
+    d = (amax / f32(127.0)).astype(f32)
+    inv = np.where(d != 0, f32(1.0) / np.where(d != 0, d, 1), f32(0.0)).astype(f32)
+    x0 = blk * inv[..., None]
+    q = np.sign(x0) * np.floor(np.abs(x0) + f32(0.5))
+    s = r16((q.sum(axis=2) * d).astype(f32))
+    return (q * r16(d)[..., None]).astype(f32).reshape(m, k), s
+
+
 class RefModel:
     """Weights decoded from a gguf written by the reference converter / quantiser."""
 
@@ -83,17 +97,35 @@ class RefModel:
         self.eps = f32(1e-6)                            # dinov2.h:33
         self.types = {n: t.ggml_type for n, t in gg.tensors.items()}
         self.w: Dict[str, np.ndarray] = {n: np.asarray(G.to_numpy(t)) for n, t in gg.tensors.items()}
+        # q4_1 / q5_1: the dot product against q8_1 activations needs q*d and the per-block minimum apart
+        self.split: Dict[str, tuple] = {n: G.dequantize_legacy(t.data, t.ne, t.ggml_type, split=True) for n, t in gg.tensors.items()
+                                        if t.ggml_type in (G.GGML_TYPE_Q4_1, G.GGML_TYPE_Q5_1)}
 
     def is_q8(self, name: str) -> bool:
         return self.types[name] == G.GGML_TYPE_Q8_0
+
+    def act_type(self, name: str) -> str:
+        """vec_dot_type of the weight's type (ggml-cpu.c:214-267): what the activation rows are converted to."""
+        t = self.types[name]
+        if t in (G.GGML_TYPE_Q8_0, G.GGML_TYPE_Q4_0, G.GGML_TYPE_Q5_0):
+            return "q8_0"
+        if t in (G.GGML_TYPE_Q4_1, G.GGML_TYPE_Q5_1):
+            return "q8_1"
+        return "f16"
 
 
 def mul_mat(model: RefModel, wname: str, x: np.ndarray) -> np.ndarray:
     """ggml_mul_mat(W, x): y[m, n] = sum_k W[n, k] * conv(x)[m, k]   (ggml-cpu.c:1266-1458)."""
     w = model.w[wname]
     w = w.reshape(w.shape[0], -1).astype(f32)
-    if model.is_q8(wname):
-        a = q8_roundtrip(x)
+    kind = model.act_type(wname)
+    if kind == "q8_0":
+        a = q8_roundtrip(x)                             # q8_0, q4_0, q5_0 weights
+    elif kind == "q8_1":
+        # q4_1 / q5_1 (ggml-cpu-quants.c vec_dot_q4_1_q8_1): sum over blocks of d_w d_a sum(q_w q_a) + m_w * s_a
+        a, s_a = q8_1_quantise(x)
+        qd, m_w = model.split[wname]
+        return a @ qd.reshape(qd.shape[0], -1).astype(f32).T + s_a @ m_w.astype(f32).T
     else:
         a = r16(x)                                      # from_float to vec_dot_type F16
     return a @ w.T

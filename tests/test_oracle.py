@@ -115,3 +115,18 @@ def test_restatement_matches_reference_live(name, H, W, classify, workdir):
     else:
         assert nmse(r["patch_tokens"], o["patch_tokens"]) < 1e-6
         assert nmse(r["cls"], o["cls"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["q4_0", "q4_1", "q5_0", "q5_1"])
+def test_restatement_legacy_quant_goldens(tag):
+    """The other four types of the reference's quantize tool (files written by that tool): weights dequantised as
+    dequantize_row_q4_0..q5_1, activations converted to q8_0 (q4_0, q5_0) or q8_1 with its fp16 block sum (q4_1, q5_1)."""
+    m = restate.RefModel(os.path.join(GOLD, f"tiny_{tag}.gguf"))
+    assert m.act_type("classifier.weight") == ("q8_1" if tag.endswith("_1") else "q8_0")
+    assert m.act_type("embeddings.patch_embeddings.projection.weight") == "f16"      # 4-D tensors are never quantised
+    img = synth.lcg_image(0, 70, 70)
+    r = restate.forward(m, img, classify=False)
+    assert nmse(r["patch_tokens"], G[f"{tag}_feat_patch"]) < TOL_Q8
+    r = restate.forward(m, img, classify=True)
+    assert nmse(r["logits"], G[f"{tag}_cls_logits"]) < 20 * TOL_Q8
+    assert int(r["probs"].argmax()) == int(G[f"{tag}_cls_probs"].argmax())
