@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
+#include "pca.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -395,6 +396,10 @@ struct dino_b200_engine {
     size_t cap_in[2] = {0, 0};
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t n_submitted = 0, n_waited = 0;
+    // PCA colouring scratch (dino_b200_pca_rgb*): mean [B][D], V / W [B][D][3], Y [B][NP][3], staging for the host variant
+    float *pca_mean = nullptr, *pca_v = nullptr, *pca_w = nullptr, *pca_y = nullptr, *pca_x = nullptr;
+    uint8_t *pca_rgb = nullptr;
+    size_t pca_cap_b = 0, pca_cap_np = 0, pca_cap_x = 0;
     int *ln_count = nullptr;          // per-128-row-block tile counters of the fused residual-GEMM + LayerNorm epilogue
     uint8_t *d_u8 = nullptr;          // raw frames for on-device preprocessing
     size_t cap_u8 = 0;
@@ -986,6 +991,9 @@ void dino_b200_destroy(dino_b200_engine *e) {
     dino::free_arena(e);
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_u8) cudaFree(e->d_u8);
+    for (void *q : {static_cast<void *>(e->pca_mean), static_cast<void *>(e->pca_v), static_cast<void *>(e->pca_w), static_cast<void *>(e->pca_y),
+                    static_cast<void *>(e->pca_x), static_cast<void *>(e->pca_rgb)})
+        if (q) cudaFree(q);
     for (int i = 0; i < 2; ++i) {
         if (e->d_in[i]) cudaFree(e->d_in[i]);
         if (e->ev_up[i]) cudaEventDestroy(e->ev_up[i]);
@@ -1157,6 +1165,89 @@ dino_b200_status dino_b200_wait(dino_b200_engine *e) {
     DINO_CUDA(cudaSetDevice(e->device));
     DINO_CUDA(cudaEventSynchronize(e->ev_done[e->n_waited & 1]));
     e->n_waited++;
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+// ------------------------------------------------------------------------------------------------ PCA colouring
+namespace dino {
+static void pca_reserve(dino_b200_engine *e, int B, int NP, bool host_staging) {
+    const int D = e->hp.hidden_size;
+    if (static_cast<size_t>(B) > e->pca_cap_b || static_cast<size_t>(NP) > e->pca_cap_np) {
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        for (float **q : {&e->pca_mean, &e->pca_v, &e->pca_w, &e->pca_y}) {
+            if (*q) DINO_CUDA(cudaFree(*q));
+            *q = nullptr;
+        }
+        if (e->pca_rgb) DINO_CUDA(cudaFree(e->pca_rgb));
+        e->pca_rgb = nullptr;
+        const size_t nb = std::max<size_t>(B, e->pca_cap_b), np = std::max<size_t>(NP, e->pca_cap_np);
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_mean), nb * D * sizeof(float)));
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_v), nb * D * 3 * sizeof(float)));
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_w), nb * D * 3 * sizeof(float)));
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_y), nb * np * 3 * sizeof(float)));
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_rgb), nb * np * 3));
+        e->pca_cap_b = nb;
+        e->pca_cap_np = np;
+    }
+    const size_t nx = static_cast<size_t>(B) * NP * D;
+    if (host_staging && nx > e->pca_cap_x) {
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->pca_x) DINO_CUDA(cudaFree(e->pca_x));
+        e->pca_x = nullptr;
+        e->pca_cap_x = 0;
+        DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->pca_x), nx * sizeof(float)));
+        e->pca_cap_x = nx;
+    }
+}
+
+// X: device [B][NP][D]; rgb: device [B][NP][3] u8 (may be null); proj: device [B][NP][3] (may be null)
+static void pca_device(dino_b200_engine *e, const float *X, int B, int NP, uint8_t *rgb, float *proj, cudaStream_t st) {
+    const int D = e->hp.hidden_size;
+    const dim3 gcol((D + 127) / 128, B);
+    pca_mean_kernel<<<gcol, 128, 0, st>>>(X, e->pca_mean, NP, D);
+    pca_init_kernel<<<gcol, 128, 0, st>>>(e->pca_w, D);
+    pca_orth_kernel<<<B, 256, 0, st>>>(e->pca_w, e->pca_v, D, 0);
+    const dim3 grow((NP + 7) / 8, B);
+    const int splits = std::max(1, std::min(16, NP / 64));
+    const int rows_per_split = (NP + splits - 1) / splits;
+    const dim3 gback((D + 127) / 128, B, splits);
+    for (int it = 0; it < PCA_ITERS; ++it) {
+        pca_project_kernel<<<grow, 256, 0, st>>>(X, e->pca_mean, e->pca_v, e->pca_y, NP, D);
+        pca_backproject_kernel<<<gback, 128, 0, st>>>(X, e->pca_mean, e->pca_y, e->pca_w, NP, D, rows_per_split);
+        pca_orth_kernel<<<B, 256, 0, st>>>(e->pca_w, e->pca_v, D, it == PCA_ITERS - 1);
+    }
+    pca_project_kernel<<<grow, 256, 0, st>>>(X, e->pca_mean, e->pca_v, e->pca_y, NP, D);
+    if (rgb) pca_to_u8_kernel<<<B, 256, 0, st>>>(e->pca_y, rgb, NP * 3);
+    DINO_CUDA(cudaGetLastError());
+    if (proj) DINO_CUDA(cudaMemcpyAsync(proj, e->pca_y, static_cast<size_t>(B) * NP * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    e->launches += 4 + 3 * PCA_ITERS + (rgb ? 1 : 0);
+}
+}  // namespace dino
+
+dino_b200_status dino_b200_pca_rgb_device(dino_b200_engine *e, const float *patch, int B, int NP, uint8_t *rgb, float *proj, void *stream) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!patch || B <= 0 || NP < 3 || (!rgb && !proj)) throw dino::StatusError(DINO_B200_ERR_INVALID, "pca_rgb: bad argument (needs at least 3 patches)");
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::pca_reserve(e, B, NP, false);
+    dino::pca_device(e, patch, B, NP, rgb, proj, stream ? static_cast<cudaStream_t>(stream) : e->stream);
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+dino_b200_status dino_b200_pca_rgb(dino_b200_engine *e, const float *patch, int B, int NP, uint8_t *rgb, float *proj) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!patch || B <= 0 || NP < 3 || (!rgb && !proj)) throw dino::StatusError(DINO_B200_ERR_INVALID, "pca_rgb: bad argument (needs at least 3 patches)");
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::pca_reserve(e, B, NP, true);
+    const size_t nx = static_cast<size_t>(B) * NP * e->hp.hidden_size;
+    DINO_CUDA(cudaMemcpyAsync(e->pca_x, patch, nx * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    dino::pca_device(e, e->pca_x, B, NP, rgb ? e->pca_rgb : nullptr, nullptr, e->stream);
+    if (rgb) DINO_CUDA(cudaMemcpyAsync(rgb, e->pca_rgb, static_cast<size_t>(B) * NP * 3, cudaMemcpyDeviceToHost, e->stream));
+    if (proj) DINO_CUDA(cudaMemcpyAsync(proj, e->pca_y, static_cast<size_t>(B) * NP * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
     return DINO_B200_OK;
     DINO_API_END(e)
 }

@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
     "dino_b200_kernel_gemm", "dino_b200_kernel_gemm_resid_ln", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
     "dino_b200_preprocess", "dino_b200_forward_u8", "dino_b200_submit", "dino_b200_wait",
+    "dino_b200_pca_rgb", "dino_b200_pca_rgb_device",
 ]
 
 
@@ -76,6 +77,8 @@ def load_library() -> C.CDLL:
     L.dino_b200_forward_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_submit.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_wait.argtypes = [vp]
+    L.dino_b200_pca_rgb.argtypes = [vp, fp, ip, ip, vp, fp]
+    L.dino_b200_pca_rgb_device.argtypes = [vp, vp, ip, ip, vp, vp, vp]
     L.dino_b200_last_error.argtypes = [vp]
     L.dino_b200_last_error.restype = C.c_char_p
     L.dino_b200_kernel_launches.argtypes = [vp]
@@ -224,6 +227,20 @@ class Engine:
     def wait(self):
         """Block until the oldest submitted batch has completed."""
         _check(load_library().dino_b200_wait(self._h), self._h)
+
+    def pca_rgb(self, patch_tokens: np.ndarray, want_proj: bool = False):
+        """PCA colouring of inference.cpp:76-86 on the device: patch_tokens float32 [B, NP, D] -> uint8 [B, NP, 3]
+        (and, optionally, the float projections [B, NP, 3])."""
+        x = np.ascontiguousarray(patch_tokens, dtype=np.float32)
+        B, NP, D = x.shape
+        assert D == self.hidden_size
+        rgb = np.empty((B, NP, 3), np.uint8)
+        proj = np.empty((B, NP, 3), np.float32) if want_proj else None
+        _check(load_library().dino_b200_pca_rgb(self._h, x.ctypes.data, B, NP, rgb.ctypes.data, _host_ptr(proj)), self._h)
+        return (rgb, proj) if want_proj else rgb
+
+    def pca_rgb_device(self, patch_ptr: int, B: int, NP: int, rgb_ptr: int = 0, proj_ptr: int = 0, stream: int = 0):
+        _check(load_library().dino_b200_pca_rgb_device(self._h, patch_ptr, B, NP, rgb_ptr or None, proj_ptr or None, stream or None), self._h)
 
     def preprocess_size(self, H: int, W: int, classify: bool):
         """Output size of the reference's preprocessing for an H x W frame (dinov2.cpp:111-116, 140-141)."""

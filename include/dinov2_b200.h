@@ -159,6 +159,17 @@ DINO_B200_API dino_b200_status dino_b200_preprocess(dino_b200_engine *e, const u
 DINO_B200_API dino_b200_status dino_b200_forward_u8(dino_b200_engine *e, const uint8_t *images, int B, int H, int W, int flags,
                                                     float *cls, float *patch, float *logits, float *probs);
 
+/* The callers' post-processing: inference.cpp:76-86 and realtime.cpp colour every patch by projecting its
+ * feature vector on the top-3 principal components of the image's NP x D patch tokens (cv::PCA DATA_AS_ROW, 3 components;
+ * pca.project) and min-max normalising the NP x 3 block to 0..255 (cv::normalize NORM_MINMAX -> CV_8U).  Done here on the
+ * device, batched: patch [B][NP][D] float32 -> rgb [B][NP][3] uint8 and/or proj [B][NP][3] float32 (either may be NULL).
+ * Components are ordered by decreasing variance; the sign of a component is arbitrary in any PCA — here the largest-
+ * magnitude loading of each is positive (OpenCV's solver leaves it as it falls, so a channel may come out inverted).
+ * _device: all pointers in device memory, asynchronous on `stream`; the plain form takes and fills host buffers. */
+DINO_B200_API dino_b200_status dino_b200_pca_rgb(dino_b200_engine *e, const float *patch, int B, int NP, uint8_t *rgb, float *proj);
+DINO_B200_API dino_b200_status dino_b200_pca_rgb_device(dino_b200_engine *e, const float *patch, int B, int NP, uint8_t *rgb,
+                                                        float *proj, void *stream);
+
 /* Replaces ggml_backend_synchronize (inference.cpp:62,66). */
 DINO_B200_API dino_b200_status dino_b200_synchronize(dino_b200_engine *e);
 
