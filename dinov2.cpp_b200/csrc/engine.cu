@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
 #include "pca.cuh"
+#include "quantize.hpp"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -982,6 +983,23 @@ dino_b200_status dino_b200_create_from_gguf(const char *path, int device, dino_b
         }
     }
     return st;
+}
+
+dino_b200_status dino_b200_quantize_gguf(const char *fname_inp, const char *fname_out, int ggml_type) {
+    if (!fname_inp || !fname_out) {
+        dino::g_last_error = "quantize_gguf: NULL argument";
+        return DINO_B200_ERR_INVALID;
+    }
+    try {
+        dino::quantize_gguf(fname_inp, fname_out, ggml_type);
+        return DINO_B200_OK;
+    } catch (const std::exception &ex) {
+        dino::g_last_error = ex.what();
+        const std::string m = ex.what();
+        if (m.rfind("cannot open", 0) == 0 || m.rfind("short", 0) == 0) return DINO_B200_ERR_IO;
+        if (m.rfind("quantize: target type", 0) == 0) return DINO_B200_ERR_INVALID;
+        return DINO_B200_ERR_FORMAT;
+    }
 }
 
 void dino_b200_destroy(dino_b200_engine *e) {

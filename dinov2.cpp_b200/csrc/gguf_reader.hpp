@@ -29,6 +29,10 @@ struct GGUFFile {
     std::map<std::string, double> kv_f;
     std::map<std::string, std::string> kv_s;
     std::vector<GGUFTensorInfo> tensors;             // file order
+    struct RawKV { std::string key; size_t off, len; };   // byte span of the whole record (key, type, value) in blob
+    std::vector<RawKV> kv_raw;                       // file order (the quantiser copies them verbatim)
+    uint32_t version = 0;
+    uint64_t alignment = 32;
 
     const GGUFTensorInfo *find(const std::string &n) const {
         for (const auto &t : tensors)
@@ -88,6 +92,7 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
     if (c.take<uint32_t>() != 0x46554747u) throw std::runtime_error("gguf: bad magic");
     const uint32_t version = c.take<uint32_t>();
     if (version != 2 && version != 3) throw std::runtime_error("gguf: unsupported version");
+    out.version = version;
     const uint64_t n_tensors = c.take<uint64_t>();
     const uint64_t n_kv = c.take<uint64_t>();
 
@@ -115,9 +120,11 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
         }
     };
     for (uint64_t i = 0; i < n_kv; ++i) {
+        const uint8_t *rec = c.p;
         const std::string key = c.str();
         const uint32_t t = c.take<uint32_t>();
         skip_or_read(skip_or_read, key, t, true);
+        out.kv_raw.push_back({key, static_cast<size_t>(rec - out.blob.data()), static_cast<size_t>(c.p - rec)});
     }
     out.tensors.resize(n_tensors);
     for (auto &t : out.tensors) {
@@ -134,6 +141,7 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
     uint64_t align = 32;
     auto it = out.kv_u.find("general.alignment");
     if (it != out.kv_u.end() && it->second) align = it->second;
+    out.alignment = align;
     const uint64_t meta = static_cast<uint64_t>(c.p - out.blob.data());
     const uint64_t data_start = (meta + align - 1) / align * align;
     for (auto &t : out.tensors) {

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
     "dino_b200_kernel_gemm", "dino_b200_kernel_gemm_resid_ln", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
     "dino_b200_preprocess", "dino_b200_forward_u8", "dino_b200_submit", "dino_b200_wait",
-    "dino_b200_pca_rgb", "dino_b200_pca_rgb_device",
+    "dino_b200_pca_rgb", "dino_b200_pca_rgb_device", "dino_b200_quantize_gguf",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library() -> C.CDLL:
     L.dino_b200_forward_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_submit.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_wait.argtypes = [vp]
+    L.dino_b200_quantize_gguf.argtypes = [C.c_char_p, C.c_char_p, ip]
     L.dino_b200_pca_rgb.argtypes = [vp, fp, ip, ip, vp, fp]
     L.dino_b200_pca_rgb_device.argtypes = [vp, vp, ip, ip, vp, vp, vp]
     L.dino_b200_last_error.argtypes = [vp]
@@ -107,6 +108,12 @@ def device_count() -> int:
 
 def _host_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
+
+
+def quantize_gguf(fname_inp: str, fname_out: str, ggml_type: int) -> None:
+    """The reference's `quantize` tool (dino_model_quantize, dinov2.cpp:354-452): host-only, works without a GPU.
+    ggml_type: 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0."""
+    _check(load_library().dino_b200_quantize_gguf(os.fsencode(fname_inp), os.fsencode(fname_out), ggml_type))
 
 
 class Engine:

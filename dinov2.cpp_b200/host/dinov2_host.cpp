@@ -324,10 +324,13 @@ struct ggml_tensor *swiglu_ffn(struct ggml_tensor *, int, struct ggml_context *,
 void forward_features(cv::Size, struct ggml_cgraph *, struct ggml_context *, const dino_model &, const dino_params &) { no_graph(__func__); }
 void forward_head(cv::Size, struct ggml_cgraph *, struct ggml_context *, const dino_model &, const dino_params &) { no_graph(__func__); }
 struct ggml_cgraph *build_graph(cv::Size, struct ggml_context *, const dino_model &, const dino_params &) { no_graph(__func__); return nullptr; }
-bool dino_model_quantize(const std::string &, const std::string &, int) {
-    fprintf(stderr, "%s: the quantiser is an offline tool outside the engine's scope; use the reference's `quantize` binary — "
-                    "its q8_0 output loads here\n", __func__);
-    return false;
+bool dino_model_quantize(const std::string &fname_inp, const std::string &fname_out, int itype) {
+    // reference dinov2.cpp:354-452, without ggml: same tensor selection, same deterministic quantisers, same file layout
+    if (dino_b200_quantize_gguf(fname_inp.c_str(), fname_out.c_str(), itype) != DINO_B200_OK) {
+        fprintf(stderr, "%s: %s\n", __func__, dino_b200_last_error(nullptr));
+        return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------

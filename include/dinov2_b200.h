@@ -170,6 +170,11 @@ DINO_B200_API dino_b200_status dino_b200_pca_rgb(dino_b200_engine *e, const floa
 DINO_B200_API dino_b200_status dino_b200_pca_rgb_device(dino_b200_engine *e, const float *patch, int B, int NP, uint8_t *rgb,
                                                         float *proj, void *stream);
 
+/* Replaces dino_model_quantize / the `quantize` tool (dinov2.cpp:354-452, quantize.cpp): host-only, needs no GPU.
+ * Re-encodes every 2-D "*weight" tensor of a F16/F32 gguf as ggml_type 2 (q4_0), 3 (q4_1), 6 (q5_0), 7 (q5_1) or 8 (q8_0)
+ * with the reference's deterministic quantisers and writes the file the reference tool would write. */
+DINO_B200_API dino_b200_status dino_b200_quantize_gguf(const char *fname_inp, const char *fname_out, int ggml_type);
+
 /* Replaces ggml_backend_synchronize (inference.cpp:62,66). */
 DINO_B200_API dino_b200_status dino_b200_synchronize(dino_b200_engine *e);
 

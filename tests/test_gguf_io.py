@@ -114,3 +114,39 @@ def test_legacy_quant_files_from_reference_quantize_tool(tag, gtype, levels):
         qd, m = G.dequantize_legacy(t.data, t.ne, gtype, split=True)
         assert np.allclose(qd.reshape(-1, 32) + m.reshape(-1, 1), deq.reshape(-1, 32), atol=1e-6)
     assert n_quant == 9          # qkv / output.dense / fc1 / fc2 of both layers + the classifier (dinov2.cpp do_quantize)
+
+
+@pytest.mark.parametrize("tag,itype", [("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q5_1", 7), ("q8_0", 8)])
+def test_quantize_gguf_reproduces_the_reference_tool(tag, itype, tmp_path):
+    """dino_b200_quantize_gguf (host-only replacement of dino_model_quantize, dinov2.cpp:354-452) against the files the
+    reference's own `quantize` binary wrote from the same input: identical container (size, KVs with the re-set ftype
+    last, trimmed tensor dims, offsets, alignment) and identical payload up to the handful of blocks where the reference
+    build's -ffast-math moves a value across a rounding boundary (one quantisation step)."""
+    out = str(tmp_path / f"mine_{tag}.gguf")
+    dinov2_b200.quantize_gguf(os.path.join(GOLD, "tiny_f16.gguf"), out, itype)
+    mine = np.fromfile(out, dtype=np.uint8)
+    ref = np.fromfile(os.path.join(GOLD, f"tiny_{tag}.gguf"), dtype=np.uint8)
+    assert mine.size == ref.size
+    differing = np.nonzero(mine != ref)[0]
+    assert differing.size <= 2e-4 * ref.size, differing.size
+    a, b = G.read_gguf(out), G.read_gguf(os.path.join(GOLD, f"tiny_{tag}.gguf"))
+    assert list(a.kv.keys()) == list(b.kv.keys()) and a.kv["ftype"] == itype
+    assert list(a.tensors.keys()) == list(b.tensors.keys())
+    for name in a.tensors:
+        ta, tb = a.tensors[name], b.tensors[name]
+        assert ta.ggml_type == tb.ggml_type and tuple(ta.ne) == tuple(tb.ne)
+        wa, wb = np.asarray(G.to_numpy(ta), np.float32), np.asarray(G.to_numpy(tb), np.float32)
+        if ta.ggml_type == itype:
+            step = np.abs(wb).max() / (7 if itype in (2, 3) else 15 if itype in (6, 7) else 127)
+            assert np.abs(wa - wb).max() <= 1.01 * step
+        else:
+            assert np.array_equal(wa, wb)
+
+
+def test_quantize_gguf_errors(tmp_path):
+    with pytest.raises(dinov2_b200.DinoB200Error):
+        dinov2_b200.quantize_gguf(os.path.join(GOLD, "tiny_f16.gguf"), str(tmp_path / "x.gguf"), 12)     # a K-quant: not offered
+    with pytest.raises(dinov2_b200.DinoB200Error):
+        dinov2_b200.quantize_gguf(str(tmp_path / "missing.gguf"), str(tmp_path / "x.gguf"), 8)
+    with pytest.raises(dinov2_b200.DinoB200Error):
+        dinov2_b200.quantize_gguf(os.path.join(GOLD, "tiny_q8_0.gguf"), str(tmp_path / "x.gguf"), 2)      # already quantised
