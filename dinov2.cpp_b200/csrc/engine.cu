@@ -153,6 +153,31 @@ static int pick_bn(int epi, int N) {
     return (N % 256 == 0) ? 256 : 128;
 }
 
+// Tile shape for one GEMM call.  Large problems (the batched path) use the widest tile the epilogue allows on CTA pairs;
+// when that leaves most SMs without a tile (single-image inference: M = 1370 rows is 6 row blocks of 256) smaller tiles /
+// single CTAs are chosen so that more SMs take part.  DINO_B200_GEMM_CG=1 forces single-CTA tiles (A/B comparisons).
+struct GemmPlan {
+    int BN, CG;
+};
+static GemmPlan plan_gemm(int epi, int M, int N) {
+    const int bn_big = pick_bn(epi, N);
+    const GemmPlan cand[3] = {{bn_big, gemm_cg()}, {bn_big, 1}, {128, 1}};
+    const int n_cand = (epi == EPI_SWIGLU_F16) ? 2 : 3;
+    GemmPlan best = cand[0];
+    int best_busy = -1;
+    for (int i = 0; i < n_cand; ++i) {
+        const GemmPlan &c = cand[i];
+        const int tiles = ((M + GEMM_BM * c.CG - 1) / (GEMM_BM * c.CG)) * ((N + c.BN - 1) / c.BN);
+        const int busy = std::min(tiles * c.CG, g_num_sms);
+        if (busy * 10 >= g_num_sms * 9) return c;   // enough work for (nearly) every SM: the widest such tile
+        if (busy > best_busy) {
+            best = c;
+            best_busy = busy;
+        }
+    }
+    return best;
+}
+
 template <int BN, int EPI, int CG>
 static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
     const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
@@ -176,12 +201,13 @@ static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 }
 
 // tmC: output map (make_tmap_out) for every epilogue except PATCH, which scatters rows and ignores it
-static void launch_gemm(int epi, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p,
+static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p,
                         cudaStream_t st) {
+    const int BN = plan.BN;
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
     if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
 #define DINO_GEMM_CASE(bn, e) \
-    if (BN == bn && epi == e) return gemm_cg() == 2 ? launch_gemm_t<bn, e, 2>(tmA, tmB, tmC, p, st) : launch_gemm_t<bn, e, 1>(tmA, tmB, tmC, p, st)
+    if (BN == bn && epi == e) return plan.CG == 2 ? launch_gemm_t<bn, e, 2>(tmA, tmB, tmC, p, st) : launch_gemm_t<bn, e, 1>(tmA, tmB, tmC, p, st)
     DINO_GEMM_CASE(256, EPI_BIAS_F16);
     DINO_GEMM_CASE(128, EPI_BIAS_F16);
     DINO_GEMM_CASE(256, EPI_GELU_F16);
@@ -351,7 +377,11 @@ struct Linear {
     __half *w = nullptr;   // [N, ldw]
     float *bias = nullptr; // [N]
     int N = 0, K = 0, ldw = 0, BN = 0;
-    CUtensorMap tm;
+    CUtensorMap tm64, tm128, tm256;    // weight tiles of 64 / 128 / 256 rows (a CTA loads BN / CG rows per k-block)
+    const CUtensorMap &tm(GemmPlan p) const {
+        const int rows = p.BN / p.CG;
+        return rows == 64 ? tm64 : rows == 128 ? tm128 : tm256;
+    }
 };
 
 struct Layer {
@@ -528,7 +558,11 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
     if (d_perm) DINO_CUDA(cudaFree(d_perm));
     L.bias = upload_f32(e, b, N, perm);
     // logical K columns = ldw: the pad columns are real zeros, so the K loop needs no tail case
-    if (want_tmap) L.tm = make_tmap_f16(L.w, L.ldw, N, L.ldw, L.BN / gemm_cg());   // each CTA of a pair loads half the rows
+    if (want_tmap) {
+        L.tm64 = make_tmap_f16(L.w, L.ldw, N, L.ldw, 64);
+        L.tm128 = make_tmap_f16(L.w, L.ldw, N, L.ldw, 128);
+        L.tm256 = make_tmap_f16(L.w, L.ldw, N, L.ldw, N >= 256 ? 256 : 128);   // 256-row tiles only exist for N % 256 == 0
+    }
 }
 
 static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) {
@@ -742,7 +776,8 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         gp.bias = e->patch.bias; gp.out = e->X; gp.ldo = D;
         gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = 1 + R;
         prof.begin(0);
-        launch_gemm(EPI_PATCH_F32, e->patch.BN, tm_ape, e->patch.tm, tmo_x, gp, st);
+        const GemmPlan pl = plan_gemm(EPI_PATCH_F32, gp.M, gp.N);
+        launch_gemm(EPI_PATCH_F32, pl, tm_ape, e->patch.tm(pl), tmo_x, gp, st);
         prof.end();
         nl++;
     }
@@ -772,7 +807,8 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = 3 * D; gp.K = D; gp.bias = ly.qkv.bias; gp.out = e->QKV; gp.ldo = 3 * D;
             prof.begin(0);
-            launch_gemm(EPI_BIAS_F16, ly.qkv.BN, tm_xn, ly.qkv.tm, tmo_qkv, gp, st);
+            const GemmPlan pl = plan_gemm(EPI_BIAS_F16, gp.M, gp.N);
+            launch_gemm(EPI_BIAS_F16, pl, tm_xn, ly.qkv.tm(pl), tmo_qkv, gp, st);
             prof.end();
         }
         prof.begin(1);
@@ -783,7 +819,9 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             gp.M = M; gp.N = D; gp.K = D; gp.bias = ly.proj.bias; gp.lscale = ly.ls1; gp.out = e->X; gp.ldo = D;
             gp.ln_gamma = ly.ln2_g; gp.ln_beta = ly.ln2_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
             prof.begin(0);
-            launch_gemm(fuse_ln ? EPI_RESID_LN_F32 : EPI_RESID_F32, ly.proj.BN, tm_ao, ly.proj.tm, tmo_x, gp, st);
+            const int epi = fuse_ln ? EPI_RESID_LN_F32 : EPI_RESID_F32;
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            launch_gemm(epi, pl, tm_ao, ly.proj.tm(pl), tmo_x, gp, st);
             prof.end();
         }
         if (!fuse_ln) {
@@ -796,7 +834,9 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = e->mlp_in; gp.K = D; gp.bias = ly.fc1.bias; gp.out = e->H1; gp.ldo = e->mlp_hidden;
             prof.begin(0);
-            launch_gemm(e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16, ly.fc1.BN, tm_xn, ly.fc1.tm, tmo_h1, gp, st);
+            const int epi = e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16;
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            launch_gemm(epi, pl, tm_xn, ly.fc1.tm(pl), tmo_h1, gp, st);
             prof.end();
         }
         {
@@ -808,7 +848,9 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
                 gp.ln_gamma = nx.ln1_g; gp.ln_beta = nx.ln1_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
             }
             prof.begin(0);
-            launch_gemm(fuse_next ? EPI_RESID_LN_F32 : EPI_RESID_F32, ly.fc2.BN, tm_h1, ly.fc2.tm, tmo_x, gp, st);
+            const int epi = fuse_next ? EPI_RESID_LN_F32 : EPI_RESID_F32;
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            launch_gemm(epi, pl, tm_h1, ly.fc2.tm(pl), tmo_x, gp, st);
             prof.end();
         }
         nl += 5;
@@ -1320,16 +1362,16 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
     configure_kernels_once();
-    const int BN = dino::pick_bn(epi, N);
+    const dino::GemmPlan pl = dino::plan_gemm(epi, M, N);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
-    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN / dino::gemm_cg());
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG);
     dino::GemmParams gp{};
     gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = out; gp.ldo = ldo;
     gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = tok_off;
     const int out_cols = epi == DINO_B200_EPI_SWIGLU_F16 ? N / 2 : N;
     const uint64_t out_rows = epi == DINO_B200_EPI_PATCH_F32 ? static_cast<uint64_t>(M / (np > 0 ? np : 1)) * ntok : static_cast<uint64_t>(M);
     const CUtensorMap tmC = dino::make_tmap_out(epi, out, out_cols, out_rows, ldo);
-    dino::launch_gemm(epi, BN, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
+    dino::launch_gemm(epi, pl, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }
@@ -1345,14 +1387,14 @@ dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const vo
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
     configure_kernels_once();
-    const int BN = dino::pick_bn(dino::EPI_RESID_LN_F32, N);
+    const dino::GemmPlan pl = dino::plan_gemm(dino::EPI_RESID_LN_F32, M, N);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
-    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, BN / dino::gemm_cg());
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG);
     dino::GemmParams gp{};
     gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = X; gp.ldo = N;
     gp.ln_gamma = gamma; gp.ln_beta = beta; gp.ln_out = static_cast<__half *>(ln_out); gp.ln_eps = eps; gp.ln_count = counters;
     const CUtensorMap tmC = dino::make_tmap_out(dino::EPI_RESID_LN_F32, X, N, M, N);
-    dino::launch_gemm(dino::EPI_RESID_LN_F32, BN, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
+    dino::launch_gemm(dino::EPI_RESID_LN_F32, pl, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }
