@@ -27,7 +27,7 @@
 
 // every AT7_POLY_MOD-th pair of probabilities is computed with a polynomial on the FMA pipe instead of MUFU (0 = none)
 #ifndef AT7_POLY_MOD
-#define AT7_POLY_MOD 6   // measured per ViT-L layer (B=64): 0 -> 828 us, 6 -> 780, 4 -> 828, 3 -> 857, 2 -> 906
+#define AT7_POLY_MOD 0   // polynomial exp2 on the FMA pipe: no gain once the softmax loop uses packed fp32 pairs (see AT7_PACKED)
 #endif
 
 namespace dino {
@@ -105,9 +105,51 @@ __device__ __forceinline__ void attn7_mask32(uint32_t (&v)[32], int valid) {
         if (i >= valid) v[i] = 0xFF800000u;
 }
 // pairs [E0, E1) of a 32-key chunk: p = exp2(s c - mc) (MUFU, every AT7_POLY_MOD-th pair on the FMA pipe), fp32 row sum,
-// one rounding to packed fp16
+// one rounding to packed fp16.  AT7_PACKED: the scale-and-shift, the row sum and the polynomial run on packed fp32 pairs
+// (FFMA2 / FADD2: one issue slot per two keys).
+#ifndef AT7_PACKED
+#define AT7_PACKED 1   // measured on v8, per ViT-L layer (B=64): scalar 769 us; packed 724 us; packed + 1/4 polynomial 725, 1/3 761, 1/2 768
+#endif
 template <int E0, int E1>
 __device__ __forceinline__ void attn7_exp_pairs(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2]) {
+#if AT7_PACKED
+    const f32x2 c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+    f32x2 acc = pack_f32x2(ls[0], ls[1]);
+#pragma unroll
+    for (int e = E0; e < E1; ++e) {
+        const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, nmc2);
+        float p0, p1;
+        if (AT7_POLY_MOD > 0 && (e % (AT7_POLY_MOD > 0 ? AT7_POLY_MOD : 1)) == AT7_POLY_MOD - 1) {
+            // exp2 on the FMA pipe, two keys per instruction: clamp, round-to-nearest split x = n + f (magic-number add), cubic
+            // for 2^f on [-0.5, 0.5], exponent patched in with one LEA per key
+            float x0, x1;
+            unpack_f32x2(x, x0, x1);
+            const f32x2 t = pack_f32x2(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
+            const f32x2 magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+            const f32x2 u = add2_f32(t, magic);
+            const f32x2 w = add2_f32(u, nmagic);
+            float w0, w1;
+            unpack_f32x2(w, w0, w1);
+            const f32x2 f = add2_f32(t, pack_f32x2(-w0, -w1));
+            f32x2 q = fma2_f32(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+            q = fma2_f32(q, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+            q = fma2_f32(q, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+            float q0, q1, u0, u1;
+            unpack_f32x2(q, q0, q1);
+            unpack_f32x2(u, u0, u1);
+            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(u0) << 23));
+            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(u1) << 23));
+        } else {
+            float x0, x1;
+            unpack_f32x2(x, x0, x1);
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+        }
+        acc = add2_f32(acc, pack_f32x2(p0, p1));
+        pk[e] = cvt_f16x2(p0, p1);
+    }
+    unpack_f32x2(acc, ls[0], ls[1]);
+#else
 #pragma unroll
     for (int e = E0; e < E1; ++e) {
         const float x0 = fmaf(__uint_as_float(v[2 * e]), c, -mc);
@@ -123,6 +165,7 @@ __device__ __forceinline__ void attn7_exp_pairs(const uint32_t (&v)[32], uint32_
         ls[e & 1] += p0 + p1;
         pk[e] = cvt_f16x2(p0, p1);
     }
+#endif
 }
 
 // Optional cycle trace of CTA 0 (compile with -DAT7_TRACE): (event id, index, clock) per role, written to p.trace

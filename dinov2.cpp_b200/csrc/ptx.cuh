@@ -361,6 +361,29 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, ui
     return (1u << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes)
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack_f32x2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2 a, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f32x2 fma2_f32(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2_f32(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
