@@ -121,8 +121,29 @@ def ensure_gguf(name: str, rank: int, barrier, quant=None) -> str:
     return path
 
 
+class stdout_to_stderr:
+    """The reference library printf()s its hyper-parameter dump (dinov2.cpp:288-299) and NCCL its version banner to fd 1;
+    stdout is reserved for the one JSON line, so those writes are sent to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def time_reference(path: str, steps: int, warmup: int, classify: bool) -> dict:
     """The reference's own CPU implementation (oracle/_ref) on one LCG image per step, all host threads."""
+    with stdout_to_stderr():
+        return _time_reference(path, steps, warmup, classify)
+
+
+def _time_reference(path: str, steps: int, warmup: int, classify: bool) -> dict:
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref as refmod
     from dinov2_b200 import synth
@@ -200,7 +221,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator comes up; stdout is reserved for the one JSON line
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
