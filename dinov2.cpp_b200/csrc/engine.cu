@@ -110,6 +110,9 @@ static int gemm_cg() {
     return v;
 }
 
+template <int EPI> static void configure_gemm_mc() {
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<256, EPI, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 2>::kSmemBytes));
+}
 template <int BN, int EPI> static void configure_gemm() {
     DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 1>::kSmemBytes));
     DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 2>::kSmemBytes));
@@ -122,6 +125,10 @@ static void configure_kernels_once() {
             int dev = 0;
             DINO_CUDA(cudaGetDevice(&dev));
             DINO_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+            configure_gemm_mc<EPI_BIAS_F16>();
+            configure_gemm_mc<EPI_GELU_F16>();
+            configure_gemm_mc<EPI_RESID_F32>();
+            configure_gemm_mc<EPI_SWIGLU_F16>();
             configure_gemm<256, EPI_BIAS_F16>();
             configure_gemm<128, EPI_BIAS_F16>();
             configure_gemm<256, EPI_GELU_F16>();
@@ -158,7 +165,16 @@ static int pick_bn(int epi, int N) {
 // single CTAs are chosen so that more SMs take part.  DINO_B200_GEMM_CG=1 forces single-CTA tiles (A/B comparisons).
 struct GemmPlan {
     int BN, CG;
+    int MC = 1;     // 2: clusters of two CTA pairs that share (TMA-multicast) the weight tile
 };
+// DINO_B200_GEMM_MC=1 enables the weight-multicast variant for the large (256-wide, CTA-pair) tiles
+static int gemm_mc() {
+    static int v = [] {
+        const char *e = getenv("DINO_B200_GEMM_MC");
+        return (e && e[0] == '1') ? 2 : 1;
+    }();
+    return v;
+}
 static GemmPlan plan_gemm(int epi, int M, int N) {
     const int bn_big = pick_bn(epi, N);
     const GemmPlan cand[3] = {{bn_big, gemm_cg()}, {bn_big, 1}, {128, 1}};
@@ -169,7 +185,13 @@ static GemmPlan plan_gemm(int epi, int M, int N) {
         const GemmPlan &c = cand[i];
         const int tiles = ((M + GEMM_BM * c.CG - 1) / (GEMM_BM * c.CG)) * ((N + c.BN - 1) / c.BN);
         const int busy = std::min(tiles * c.CG, g_num_sms);
-        if (busy * 10 >= g_num_sms * 9) return c;   // enough work for (nearly) every SM: the widest such tile
+        if (busy * 10 >= g_num_sms * 9) {           // enough work for (nearly) every SM: the widest such tile
+            GemmPlan r = c;
+            if (i == 0 && c.CG == 2 && c.BN == 256 && gemm_mc() == 2 && g_num_sms % 4 == 0 && epi != EPI_PATCH_F32 &&
+                epi != EPI_RESID_LN_F32 && tiles >= g_num_sms)
+                r.MC = 2;
+            return r;
+        }
         if (busy > best_busy) {
             best = c;
             best_busy = busy;
@@ -178,13 +200,13 @@ static GemmPlan plan_gemm(int epi, int M, int N) {
     return best;
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int MC = 1>
 static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
-    const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
+    const int tiles = ((p.M + GEMM_BM * CG * MC - 1) / (GEMM_BM * CG * MC)) * ((p.N + BN - 1) / BN);   // per cluster
     // DINO_B200_GEMM_SMS=n restricts the persistent grid to n SMs (experiments: per-SM throughput vs L2 bandwidth share)
     static const int sm_cap = [] { const char *e = getenv("DINO_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();
     const int sms = sm_cap > 0 ? std::min(sm_cap, g_num_sms) : g_num_sms;
-    const int grid = std::max(1, std::min(tiles, sms / CG)) * CG;      // persistent: one CTA (pair) per SM (pair)
+    const int grid = std::max(1, std::min(tiles, sms / (CG * MC))) * CG * MC;      // persistent: one cluster per CG * MC SMs
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -192,18 +214,25 @@ static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CG * MC;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DINO_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05<BN, EPI, CG>, tmA, tmB, tmC, p));
+    DINO_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05<BN, EPI, CG, MC>, tmA, tmB, tmC, p));
 }
 
 // tmC: output map (make_tmap_out) for every epilogue except PATCH, which scatters rows and ignores it
 static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p,
                         cudaStream_t st) {
     const int BN = plan.BN;
+    if (plan.MC == 2) {
+        if (epi == EPI_BIAS_F16) return launch_gemm_t<256, EPI_BIAS_F16, 2, 2>(tmA, tmB, tmC, p, st);
+        if (epi == EPI_GELU_F16) return launch_gemm_t<256, EPI_GELU_F16, 2, 2>(tmA, tmB, tmC, p, st);
+        if (epi == EPI_RESID_F32) return launch_gemm_t<256, EPI_RESID_F32, 2, 2>(tmA, tmB, tmC, p, st);
+        if (epi == EPI_SWIGLU_F16) return launch_gemm_t<256, EPI_SWIGLU_F16, 2, 2>(tmA, tmB, tmC, p, st);
+        throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no multicast kernel for this epilogue");
+    }
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
     if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
 #define DINO_GEMM_CASE(bn, e) \
@@ -379,7 +408,7 @@ struct Linear {
     int N = 0, K = 0, ldw = 0, BN = 0;
     CUtensorMap tm64, tm128, tm256;    // weight tiles of 64 / 128 / 256 rows (a CTA loads BN / CG rows per k-block)
     const CUtensorMap &tm(GemmPlan p) const {
-        const int rows = p.BN / p.CG;
+        const int rows = p.BN / p.CG / p.MC;
         return rows == 64 ? tm64 : rows == 128 ? tm128 : tm256;
     }
 };
@@ -1364,7 +1393,7 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     configure_kernels_once();
     const dino::GemmPlan pl = dino::plan_gemm(epi, M, N);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
-    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG);
+    const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG / pl.MC);
     dino::GemmParams gp{};
     gp.M = M; gp.N = N; gp.K = K; gp.bias = bias; gp.lscale = lscale; gp.out = out; gp.ldo = ldo;
     gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = tok_off;

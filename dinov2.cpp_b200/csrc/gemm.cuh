@@ -89,12 +89,17 @@ __device__ __forceinline__ float silu_f32(float x) {
     return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
 
-template <int BN, int EPI, int CG>
+// MC = 2 (only with CG = 2): clusters of FOUR CTAs = two CTA pairs that work on the same weight tile and on vertically adjacent
+// 256-row blocks of A.  Every CTA fetches a quarter of the 256 x 64 weight tile per k-block and TMA-multicasts it to the
+// CTA that holds the same half in the other pair, so the weight bytes cross the L2 -> SM fabric once per cluster instead of
+// once per pair (-25 % operand traffic per FLOP).  A stage is refilled only after BOTH pairs' MMAs have released it.
+template <int BN, int EPI, int CG, int MC = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
     static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
+    static_assert(MC == 1 || (MC == 2 && CG == 2), "weight multicast couples two CTA pairs");
     static_assert(EPI != EPI_SWIGLU_F16 || BN == 256, "SwiGLU tiles pair 128 gate + 128 up columns");
     constexpr int kStages = Cfg::kStages;
 
@@ -114,13 +119,16 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);       // tiles of 128*CG rows
+    const int num_m = (p.M + GEMM_BM * CG * MC - 1) / (GEMM_BM * CG * MC);   // row blocks of 128 * CG * MC rows (one per cluster)
     const int num_n = (p.N + BN - 1) / BN;
     const int num_k = (p.K + GEMM_BK - 1) / GEMM_BK;
     const int num_tiles = num_m * num_n;
-    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;         // 0 = leader (issues the MMAs)
-    const int tile0 = static_cast<int>(blockIdx.x) / CG;                // first tile of this CTA (pair)
-    const int tile_step = static_cast<int>(gridDim.x) / CG;
+    const uint32_t cluster_rank = CG == 2 ? cluster_ctarank() : 0u;     // rank in the cluster of CG * MC CTAs
+    const uint32_t cta_rank = cluster_rank & 1u;                        // rank in the CTA pair: 0 = leader (issues the MMAs)
+    const uint32_t pair_idx = cluster_rank >> 1;                        // which pair of the cluster (MC = 2)
+    const uint32_t leader_rank = cluster_rank & ~1u;                    // cluster rank of this pair's leader
+    const int tile0 = static_cast<int>(blockIdx.x) / (CG * MC);         // first tile of this cluster
+    const int tile_step = static_cast<int>(gridDim.x) / (CG * MC);
 
     if (warp == 10 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -130,7 +138,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 11 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], CG);                      // pair: the leader's own expect_tx arrive + the peer's arrive
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], MC);                      // multicast: both pairs' MMA warps release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
@@ -156,18 +164,26 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t ph = 0;
         for (int t = tile0; t < num_tiles; t += tile_step) {
             const int m_blk = t / num_n, n_blk = t % num_n;
-            const int row_a = (m_blk * CG + static_cast<int>(cta_rank)) * GEMM_BM;          // this CTA's 128 A rows
+            const int row_a = ((m_blk * MC + static_cast<int>(pair_idx)) * CG + static_cast<int>(cta_rank)) * GEMM_BM;   // this CTA's 128 A rows
             const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (BN / CG);          // this CTA's share of the weight rows
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (elect_one()) {
                     // activations are streamed once per N tile (evict first); weights are shared by every CTA
                     if constexpr (CG == 2) {
-                        const uint32_t full0 = mapa_shared(&full_bar[s], 0);                 // the leader's barrier counts both CTAs' bytes
+                        const uint32_t full0 = mapa_shared(&full_bar[s], leader_rank);       // the leader's barrier counts both CTAs' bytes
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
                         else mbar_arrive_cluster(full0);
                         tma_load_2d_2sm(smem_a + s * Cfg::kABytes, &tmA, full0, kb * GEMM_BK, row_a, kEvictFirst);
-                        tma_load_2d_2sm(smem_b + s * Cfg::kBBytes, &tmB, full0, kb * GEMM_BK, row_b, kEvictLast);
+                        if constexpr (MC == 2) {
+                            // this CTA's quarter of the weight tile, delivered to itself and to its counterpart in the other pair
+                            constexpr int kQRows = BN / CG / MC;
+                            const uint16_t mask = static_cast<uint16_t>((1u << cluster_rank) | (1u << (cluster_rank ^ 2u)));
+                            tma_load_2d_2sm_mc(smem_b + s * Cfg::kBBytes + pair_idx * (kQRows * GEMM_BK * 2), &tmB, full0, kb * GEMM_BK,
+                                               row_b + static_cast<int>(pair_idx) * kQRows, mask, kEvictLast);
+                        } else {
+                            tma_load_2d_2sm(smem_b + s * Cfg::kBBytes, &tmB, full0, kb * GEMM_BK, row_b, kEvictLast);
+                        }
                     } else {
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                         tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, row_a, kEvictFirst);
@@ -218,8 +234,9 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         // frees the smem stage (in both CTAs of a pair) once these MMAs retire; after the last k-block the
                         // accumulator is complete -> epilogue warps (of both CTAs)
                         if constexpr (CG == 2) {
-                            umma_commit_2sm(&empty_bar[s], 3);
-                            if (kb == num_k - 1) umma_commit_2sm(&tmem_full[as], 3);
+                            // the stage is released in every CTA that wrote into this pair's shared memory (multicast: all four)
+                            umma_commit_2sm(&empty_bar[s], MC == 2 ? 0xF : 3);
+                            if (kb == num_k - 1) umma_commit_2sm(&tmem_full[as], static_cast<uint16_t>(3u << leader_rank));
                         } else {
                             umma_commit(&empty_bar[s]);
                             if (kb == num_k - 1) umma_commit(&tmem_full[as]);
@@ -292,7 +309,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
-            const int row0 = (m_blk * CG + static_cast<int>(cta_rank)) * GEMM_BM + q * 32;   // first row of this warp's 32-row slab
+            const int row0 = ((m_blk * MC + static_cast<int>(pair_idx)) * CG + static_cast<int>(cta_rank)) * GEMM_BM + q * 32;   // first row of this warp's 32-row slab
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
             if constexpr (EPI == EPI_SWIGLU_F16) {
@@ -417,7 +434,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], 0));   // the leader's MMA warp waits on it
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(&tmem_empty[as], leader_rank));   // the leader's MMA warp waits on it
                 else mbar_arrive(&tmem_empty[as]);
             }
             if constexpr (EPI == EPI_RESID_LN_F32) {
@@ -425,7 +442,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // its last tile, normalised) one tile LATER, when its reduce-adds have certainly been performed: waiting for
                 // them right here would put an L2 round trip into every tile's epilogue.
                 if (ln_pending >= 0) ln_publish(ln_pending, false);
-                ln_pending = m_blk * CG + static_cast<int>(cta_rank);
+                ln_pending = (m_blk * MC + static_cast<int>(pair_idx)) * CG + static_cast<int>(cta_rank);
             }
         }
         if constexpr (EPI == EPI_RESID_LN_F32) {

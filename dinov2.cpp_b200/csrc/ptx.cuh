@@ -308,6 +308,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMa
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+// same, multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask` (16-bit mask of cluster ranks);
+// the bytes are counted on the mbarrier at bar_cluster_addr's offset in the pair leader of each destination CTA
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void *smem_dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1,
+                                                   uint16_t cta_mask, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+        "[%0], [%1, {%4, %5}], [%2], %3, %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t *smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");

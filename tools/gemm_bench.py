@@ -12,7 +12,7 @@ if len(sys.argv) > 1:
 torch.manual_seed(0)
 M = 64 * 1370
 shapes = [("qkv", E.EPI_BIAS_F16, 3072, 1024), ("proj", E.EPI_RESID_F32, 1024, 1024), ("fc1", E.EPI_GELU_F16, 4096, 1024), ("fc2", E.EPI_RESID_F32, 1024, 4096)]
-tag = f"sms={os.environ.get('DINO_B200_GEMM_SMS','all')} cg={os.environ.get('DINO_B200_GEMM_CG','2')} lib={os.path.basename(E.LIB_PATH)}"
+tag = f"sms={os.environ.get('DINO_B200_GEMM_SMS','all')} cg={os.environ.get('DINO_B200_GEMM_CG','2')} mc={os.environ.get('DINO_B200_GEMM_MC','0')} lib={os.path.basename(E.LIB_PATH)}"
 for name, epi, N, K in shapes:
     A = (torch.randn(M, K, device="cuda") * 0.5).half()
     W = (torch.randn(N, K, device="cuda") * 0.05).half()
@@ -25,9 +25,25 @@ for name, epi, N, K in shapes:
     for _ in range(3):
         run()
     torch.cuda.synchronize()
-    if name == "qkv":
-        ref = (A[:512].float() @ W.float().t() + bias)
-        print(f"check {name}: max_abs {float((out[:512].float() - ref).abs().max()):.3e}", flush=True)
+    if not f32:
+        worst = 0.0
+        for r0 in (0, 300, M // 2 - 77, M - 512):          # windows at the start, across tile borders, at the ragged end
+            ref = (A[r0:r0 + 512].float() @ W.float().t() + bias)
+            if epi == E.EPI_GELU_F16:
+                v = ref.half().float()
+                ref = 0.5 * v * (1 + torch.tanh(0.7978845608028654 * v * (1 + 0.044715 * v * v)))
+            worst = max(worst, float((out[r0:r0 + 512].float() - ref).abs().max()))
+        print(f"check {name}: max_abs over 4 row windows {worst:.3e}", flush=True)
+    else:
+        X0 = torch.randn(M, N, device="cuda")
+        out.copy_(X0)
+        run()
+        torch.cuda.synchronize()
+        worst = 0.0
+        for r0 in (0, 300, M // 2 - 77, M - 512):
+            ref = X0[r0:r0 + 512] + ls * (A[r0:r0 + 512].float() @ W.float().t() + bias)
+            worst = max(worst, float((out[r0:r0 + 512] - ref).abs().max()))
+        print(f"check {name}: max_abs over 4 row windows {worst:.3e}", flush=True)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 20
     a.record()
