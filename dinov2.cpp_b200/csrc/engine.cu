@@ -454,7 +454,10 @@ struct dino_b200_engine {
     cudaStream_t copy_stream = nullptr;
     float *d_in[2] = {nullptr, nullptr};
     size_t cap_in[2] = {0, 0};
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_fwd[2] = {nullptr, nullptr};
+    cudaStream_t d2h_stream = nullptr;                  // read-backs run under the NEXT batch's forward pass
+    float *r_buf[2] = {nullptr, nullptr};               // per-slot device results: cls | logits | probs | patch tokens
+    size_t cap_r[2] = {0, 0};
     uint64_t n_submitted = 0, n_waited = 0;
     // PCA colouring scratch (dino_b200_pca_rgb*): mean [B][D], V / W [B][D][3], Y [B][NP][3], staging for the host variant
     float *pca_mean = nullptr, *pca_v = nullptr, *pca_w = nullptr, *pca_y = nullptr, *pca_x = nullptr;
@@ -1087,8 +1090,11 @@ void dino_b200_destroy(dino_b200_engine *e) {
         if (e->d_in[i]) cudaFree(e->d_in[i]);
         if (e->ev_up[i]) cudaEventDestroy(e->ev_up[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+        if (e->ev_fwd[i]) cudaEventDestroy(e->ev_fwd[i]);
+        if (e->r_buf[i]) cudaFree(e->r_buf[i]);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     for (auto &pe : e->prof) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto &pe : e->prof_pool) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -1198,20 +1204,27 @@ dino_b200_status dino_b200_submit(dino_b200_engine *e, const float *images, int 
     const int slot = static_cast<int>(e->n_submitted & 1);
     if (!e->copy_stream) {
         DINO_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        DINO_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             DINO_CUDA(cudaEventCreateWithFlags(&e->ev_up[i], cudaEventDisableTiming));
             DINO_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_fwd[i], cudaEventDisableTiming));
         }
     }
     const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
     const size_t np = static_cast<size_t>(H / ps) * (W / ps);
     const size_t n_in = static_cast<size_t>(B) * 3 * H * W;
     const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    if (classify && !e->wc) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit: checkpoint has no classifier head");
+    // per-slot device results, so that the read-back of batch k (own stream) may run under the forward pass of batch k+1
+    const size_t n_cls = cls ? static_cast<size_t>(B) * D : 0, n_log = (classify && logits) ? static_cast<size_t>(B) * C : 0;
+    const size_t n_prob = (classify && probs) ? static_cast<size_t>(B) * C : 0, n_patch = patch ? static_cast<size_t>(B) * np * D : 0;
+    const size_t n_res = n_cls + n_log + n_prob + n_patch;
     // anything that (re)allocates waits for the work in flight first
-    const bool grow = n_in > e->cap_in[slot] || (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch);
-    if (grow) {
+    if (n_in > e->cap_in[slot] || n_res > e->cap_r[slot]) {
         DINO_CUDA(cudaStreamSynchronize(e->copy_stream));
         DINO_CUDA(cudaStreamSynchronize(e->stream));
+        DINO_CUDA(cudaStreamSynchronize(e->d2h_stream));
         if (n_in > e->cap_in[slot]) {
             if (e->d_in[slot]) DINO_CUDA(cudaFree(e->d_in[slot]));
             e->d_in[slot] = nullptr;
@@ -1219,29 +1232,34 @@ dino_b200_status dino_b200_submit(dino_b200_engine *e, const float *images, int 
             DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->d_in[slot]), n_in * sizeof(float)));
             e->cap_in[slot] = n_in;
         }
-        if (patch && static_cast<size_t>(B) * np * D > e->cap_o_patch) {
-            if (e->o_patch) DINO_CUDA(cudaFree(e->o_patch));
-            e->o_patch = nullptr;
-            e->cap_o_patch = 0;
-            DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->o_patch), static_cast<size_t>(B) * np * D * sizeof(float)));
-            e->cap_o_patch = static_cast<size_t>(B) * np * D;
+        if (n_res > e->cap_r[slot]) {
+            if (e->r_buf[slot]) DINO_CUDA(cudaFree(e->r_buf[slot]));
+            e->r_buf[slot] = nullptr;
+            e->cap_r[slot] = 0;
+            DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->r_buf[slot]), n_res * sizeof(float)));
+            e->cap_r[slot] = n_res;
         }
     }
     dino::ensure_arena(e, B, H, W);     // synchronises the engine stream itself when it has to grow
+    float *r_cls = e->r_buf[slot], *r_log = r_cls + n_cls, *r_prob = r_log + n_log, *r_patch = r_prob + n_prob;
     cudaStream_t st = e->stream;
-    // the slot's previous forward pass (batch k-2) has been waited for by the caller or is ordered before us on `st`;
-    // the upload must not overwrite the slot while that forward still reads it
-    if (e->n_submitted >= 2) DINO_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+    // slot reuse (batch k-2): its forward pass has read the input slot and its read-back has left the result slot
+    if (e->n_submitted >= 2) {
+        DINO_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+        DINO_CUDA(cudaStreamWaitEvent(st, e->ev_done[slot], 0));
+    }
     DINO_CUDA(cudaMemcpyAsync(e->d_in[slot], images, n_in * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
     DINO_CUDA(cudaEventRecord(e->ev_up[slot], e->copy_stream));
     DINO_CUDA(cudaStreamWaitEvent(st, e->ev_up[slot], 0));
-    dino::forward_device(e, e->d_in[slot], layout, B, H, W, flags, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
-                         (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
-    if (cls) DINO_CUDA(cudaMemcpyAsync(cls, e->o_cls, static_cast<size_t>(B) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (patch) DINO_CUDA(cudaMemcpyAsync(patch, e->o_patch, static_cast<size_t>(B) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits, e->logits, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs, e->probs, static_cast<size_t>(B) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
-    DINO_CUDA(cudaEventRecord(e->ev_done[slot], st));
+    dino::forward_device(e, e->d_in[slot], layout, B, H, W, flags, n_cls ? r_cls : nullptr, n_patch ? r_patch : nullptr,
+                         n_log ? r_log : nullptr, n_prob ? r_prob : nullptr, st);
+    DINO_CUDA(cudaEventRecord(e->ev_fwd[slot], st));
+    DINO_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->ev_fwd[slot], 0));
+    if (n_cls) DINO_CUDA(cudaMemcpyAsync(cls, r_cls, n_cls * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_patch) DINO_CUDA(cudaMemcpyAsync(patch, r_patch, n_patch * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_log) DINO_CUDA(cudaMemcpyAsync(logits, r_log, n_log * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_prob) DINO_CUDA(cudaMemcpyAsync(probs, r_prob, n_prob * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    DINO_CUDA(cudaEventRecord(e->ev_done[slot], e->d2h_stream));
     e->n_submitted++;
     return DINO_B200_OK;
     DINO_API_END(e)

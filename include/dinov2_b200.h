@@ -137,7 +137,7 @@ DINO_B200_API dino_b200_status dino_b200_forward_device(dino_b200_engine *e, con
 /* Pipelined form of dino_b200_forward for a stream of batches (what realtime.cpp's capture loop needs, realtime.cpp:75-101):
  * submit() enqueues the upload of the batch, its forward pass and the read-back of the requested outputs and returns at once;
  * wait() blocks until the OLDEST submitted batch has completed and its outputs are in place.  Up to two batches may be in
- * flight: the upload of batch k+1 (copy engine) runs under the forward pass of batch k.  `images` and the output buffers
+* flight: the upload of batch k+1 and the read-back of batch k-1 (two copy streams) run under the forward pass of batch k.  `images` and the output buffers
  * must stay valid (and should be pinned host memory for the overlap to be real) until the matching wait() returns. */
 DINO_B200_API dino_b200_status dino_b200_submit(dino_b200_engine *e, const float *images, int layout, int B, int H, int W,
                                                 int flags, float *cls, float *patch, float *logits, float *probs);
