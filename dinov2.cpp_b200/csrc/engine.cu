@@ -223,8 +223,21 @@ static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 }
 
 // tmC: output map (make_tmap_out) for every epilogue except PATCH, which scatters rows and ignores it
-static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p,
+static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p_in,
                         cudaStream_t st) {
+    // DINO_B200_GEMM_AHINT / DINO_B200_GEMM_BHINT = first|normal|last override the L2 eviction hints of the activation / weight
+    // loads (defaults: normal / last; measured in tools/gemm_bench.py)
+    auto hint_of = [](const char *name) -> unsigned long long {
+        const char *e = getenv(name);
+        if (e && e[0] == 'f') return kEvictFirst;
+        if (e && e[0] == 'n') return kEvictNormal;
+        if (e && e[0] == 'l') return kEvictLast;
+        return 0ull;
+    };
+    static const unsigned long long a_hint = hint_of("DINO_B200_GEMM_AHINT"), b_hint = hint_of("DINO_B200_GEMM_BHINT");
+    GemmParams p = p_in;
+    if (!p.a_hint) p.a_hint = a_hint;
+    if (!p.b_hint) p.b_hint = b_hint;
     const int BN = plan.BN;
     if (plan.MC == 2) {
         if (epi == EPI_BIAS_F16) return launch_gemm_t<256, EPI_BIAS_F16, 2, 2>(tmA, tmB, tmC, p, st);

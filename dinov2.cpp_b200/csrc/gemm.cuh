@@ -51,6 +51,8 @@ struct GemmParams {
     __half *ln_out;
     float ln_eps;
     int *ln_count;          // one counter per 128-row block, zero on entry and zero again on exit
+    unsigned long long a_hint;   // L2 eviction-priority hints of the A (activation) / W (weight) loads; 0 = default (normal / evict-last)
+    unsigned long long b_hint;
 };
 
 constexpr int GEMM_BM = 128;
@@ -162,6 +164,11 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // lane issues the copies.
         int s = 0;
         uint32_t ph = 0;
+        // Activations: NO evict-first — an A block is re-read by the other column tiles of its row block over several waves, and
+        // the streaming output stores would push evict-first lines out in between (measured: fc1 fetched its A operand ~4 times
+        // from DRAM, every GEMM 3-4 % slower).  Weights are shared by every CTA for the whole launch: evict-last.
+        const uint64_t a_hint = p.a_hint ? p.a_hint : kEvictNormal;
+        const uint64_t b_hint = p.b_hint ? p.b_hint : kEvictLast;
         for (int t = tile0; t < num_tiles; t += tile_step) {
             const int m_blk = t / num_n, n_blk = t % num_n;
             const int row_a = ((m_blk * MC + static_cast<int>(pair_idx)) * CG + static_cast<int>(cta_rank)) * GEMM_BM;   // this CTA's 128 A rows
@@ -169,25 +176,24 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (elect_one()) {
-                    // activations are streamed once per N tile (evict first); weights are shared by every CTA
                     if constexpr (CG == 2) {
                         const uint32_t full0 = mapa_shared(&full_bar[s], leader_rank);       // the leader's barrier counts both CTAs' bytes
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
                         else mbar_arrive_cluster(full0);
-                        tma_load_2d_2sm(smem_a + s * Cfg::kABytes, &tmA, full0, kb * GEMM_BK, row_a, kEvictFirst);
+                        tma_load_2d_2sm(smem_a + s * Cfg::kABytes, &tmA, full0, kb * GEMM_BK, row_a, a_hint);
                         if constexpr (MC == 2) {
                             // this CTA's quarter of the weight tile, delivered to itself and to its counterpart in the other pair
                             constexpr int kQRows = BN / CG / MC;
                             const uint16_t mask = static_cast<uint16_t>((1u << cluster_rank) | (1u << (cluster_rank ^ 2u)));
                             tma_load_2d_2sm_mc(smem_b + s * Cfg::kBBytes + pair_idx * (kQRows * GEMM_BK * 2), &tmB, full0, kb * GEMM_BK,
-                                               row_b + static_cast<int>(pair_idx) * kQRows, mask, kEvictLast);
+                                               row_b + static_cast<int>(pair_idx) * kQRows, mask, b_hint);
                         } else {
-                            tma_load_2d_2sm(smem_b + s * Cfg::kBBytes, &tmB, full0, kb * GEMM_BK, row_b, kEvictLast);
+                            tma_load_2d_2sm(smem_b + s * Cfg::kBBytes, &tmB, full0, kb * GEMM_BK, row_b, b_hint);
                         }
                     } else {
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                        tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, row_a, kEvictFirst);
-                        tma_load_2d_hint(smem_b + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * GEMM_BK, row_b, kEvictLast);
+                        tma_load_2d_hint(smem_a + s * Cfg::kABytes, &tmA, &full_bar[s], kb * GEMM_BK, row_a, a_hint);
+                        tma_load_2d_hint(smem_b + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * GEMM_BK, row_b, b_hint);
                     }
                 }
                 __syncwarp();

@@ -115,6 +115,7 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
 // same with an L2 eviction-priority hint (createpolicy-encoded constants, as CUTLASS' CacheHintSm90)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 __device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0,
                                                  int32_t c1, uint64_t hint) {
     asm volatile(
