@@ -75,7 +75,8 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 // Row-major [rows, cols] tensor with row stride ld (elements); box = box_cols x box_rows with box_cols * elem = 128 B,
 // 128-B swizzle; out-of-bounds elements read as zero / are clipped on store.
-static CUtensorMap make_tmap_2d(const void *ptr, bool f32, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+static CUtensorMap make_tmap_2d(const void *ptr, bool f32, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                                CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     CUtensorMap m;
     const size_t es = f32 ? sizeof(float) : sizeof(__half);
     const cuuint64_t gdim[2] = {cols, rows};
@@ -85,10 +86,23 @@ static CUtensorMap make_tmap_2d(const void *ptr, bool f32, uint64_t cols, uint64
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstride[0] & 15)) throw CudaError("TMA operand is not 16-byte aligned");
     const CUresult r = get_encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                                        const_cast<void *>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, promo,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
     return m;
+}
+// The attention kernel's view of QKV: 128-byte row segments (one head's 64 dims) 6*D bytes apart.  Promoting those to
+// 256-byte L2 fetches (right for the GEMM operands, whose next k-block is the neighbouring 128 bytes) would drag in the
+// NEXT head's data, which is evicted again before its turn: DINO_B200_ATTN_PROMO=256 restores that for A/B comparisons.
+static CUtensorMapL2promotion attn_promotion() {
+    static const CUtensorMapL2promotion v = [] {
+        const char *e = getenv("DINO_B200_ATTN_PROMO");
+        if (e && e[0] == '2') return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        if (e && e[0] == '0') return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        if (e && e[0] == '6') return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
+    return v;
 }
 static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
     return make_tmap_2d(ptr, false, cols, rows, ld, box_rows);
@@ -800,7 +814,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
     const CUtensorMap tm_xn = make_tmap_f16(e->Xn, D, M, D, GEMM_BM);
     const CUtensorMap tm_ao = make_tmap_f16(e->AO, D, M, D, GEMM_BM);
     const CUtensorMap tm_h1 = make_tmap_f16(e->H1, e->mlp_hidden, M, e->mlp_hidden, GEMM_BM);
-    const CUtensorMap tm_qkv = make_tmap_f16(e->QKV, 3 * D, M, 3 * D, ATT_BKV);
+    const CUtensorMap tm_qkv = make_tmap_2d(e->QKV, false, 3 * D, M, 3 * D, ATT_BKV, attn_promotion());
     const CUtensorMap tmo_qkv = make_tmap_out(EPI_BIAS_F16, e->QKV, 3 * D, M, 3 * D);
     const CUtensorMap tmo_h1 = make_tmap_out(EPI_GELU_F16, e->H1, e->mlp_hidden, M, e->mlp_hidden);
     const CUtensorMap tmo_x = make_tmap_out(EPI_RESID_F32, e->X, D, M, D);
@@ -1466,7 +1480,7 @@ dino_b200_status dino_b200_kernel_attention(const void *qkv, void *out, int B, i
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
     configure_kernels_once();
-    const CUtensorMap tm = dino::make_tmap_f16(qkv, 3 * D, static_cast<uint64_t>(B) * n_tok, 3 * D, ATT_BKV);
+    const CUtensorMap tm = dino::make_tmap_2d(qkv, false, 3 * D, static_cast<uint64_t>(B) * n_tok, 3 * D, ATT_BKV, dino::attn_promotion());
     dino::launch_attention(tm, static_cast<__half *>(out), B, n_tok, D, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
