@@ -184,6 +184,15 @@ def test_full_size_properties_vitl14(workdir):
     bet = gguf_io.to_numpy(gg.tensors["layernorm.bias"])
     z = (a["patch_tokens"][0] - bet) / gam
     assert np.abs(z.mean(axis=1)).max() < 1e-3 and np.abs(z.var(axis=1) - 1).max() < 1e-2
+    # and, where the reference build travelled to this box, the reference itself on one image of the headline model
+    # (24 layers of accumulated rounding: same tolerances as every other f16 case)
+    if refmod.available():
+        R = refmod.Reference(p, classify=True, H=518, W=518)
+        o = R.forward(imgs[0])
+        R.close()
+        assert int(a["probs"][0].argmax()) == int(o["probs"].argmax())
+        assert nmse(a["logits"][0], o["logits"]) < NMSE_F16
+        assert nmse(a["probs"][0], o["probs"]) < NMSE_F16
 
 
 @pytest.mark.parametrize("tag", ["q4_0", "q4_1", "q5_0", "q5_1"])
