@@ -1,5 +1,6 @@
 // Fused multi-head self-attention, third generation: persistent, output accumulator resident in TMEM.
-// Contract as attention.cuh / attention2.cuh (replaces the reference's mul_mat(K,Q) -> soft_max_ext -> mul_mat(V,P)
+// Kept as the previous round's baseline for A/B runs (DINO_B200_ATTN=3).  Contract (every generation): replaces the
+// reference's mul_mat(K,Q) -> soft_max_ext -> mul_mat(V,P)
 // chain, dinov2.cpp:479-543; head_dim 64, no mask).  What changed against v2, and why:
 //
 //  * Persistent CTAs (grid = #SMs) walk a static list of work items (image, head, 256-query block).  TMEM allocation,

@@ -5,12 +5,9 @@
 // entry point fails with DINO_B200_ERR_NO_DEVICE.
 #include "../../include/dinov2_b200.h"
 
-#include "attention.cuh"
-#include "attention2.cuh"
+#include "attention_common.cuh"
 #include "attention3.cuh"
-#include "attention4.cuh"
 #include "attention5.cuh"
-#include "attention6.cuh"
 #include "attention7.cuh"
 #include "attention8.cuh"
 #include "elementwise.cuh"
@@ -154,12 +151,8 @@ static void configure_kernels_once() {
             configure_gemm<256, EPI_SWIGLU_F16>();
             configure_gemm<256, EPI_PATCH_F32>();
             configure_gemm<128, EPI_PATCH_F32>();
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, AT6_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
             DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM_BYTES));
         } catch (const std::exception &e) {
@@ -279,13 +272,14 @@ static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CU
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=1..7 selects another generation of the attention kernel for A/B comparisons (default: 8 = v5's TMEM ring
-// with intra-tile pipelining).  Per ViT-L layer at batch 64 on B200: v3 932 us, v4 885, v5 780, v6 (16 softmax warps) 872,
-// v7 (loads pipelined across tiles) 878, v8 768.
+// DINO_B200_ATTN=3|5|7 selects another generation of the attention kernel for A/B comparisons (default: 8 = v5's TMEM ring
+// with intra-tile pipelining and packed-pair softmax arithmetic).  Per ViT-L layer at batch 64 on B200: v3 932 us, v4 885,
+// v5 780, v6 (16 softmax warps) 872, v7 (loads pipelined across tiles) 878, v8 724.  v1, v2, v4 and v6 were removed from the
+// tree after measurement (git history: attention.cuh, attention2.cuh, attention4.cuh, attention6.cuh).
 static int attention_variant() {
     static int v = [] {
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 8;
+        return (e && (e[0] == '3' || e[0] == '5' || e[0] == '7')) ? e[0] - '0' : 8;
     }();
     return v;
 }
@@ -306,23 +300,7 @@ static unsigned long long *attention_trace_buffer(cudaStream_t st) {
 
 static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, cudaStream_t st) {
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
-    if (attention_variant() == 1) {
-        AttnParams ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        const dim3 grid((n_tok + ATT_BQ - 1) / ATT_BQ, D / ATT_HD, B);
-        attention_fwd_tcgen05<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 2) {
-        Attn2Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        const dim3 grid((n_tok + 255) / 256, D / ATT_HD, B);
-        attention_fwd_v2<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 8) {
+    if (attention_variant() == 8) {
         Attn8Params ap;
         ap.n_tok = n_tok;
         ap.hidden = D;
@@ -352,21 +330,6 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
 #endif
         const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
         attention_fwd_v7<<<grid, AT7_THREADS, AT7_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 6) {
-        Attn6Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        ap.trace = nullptr;
-#ifdef AT6_TRACE
-        ap.trace = attention_trace_buffer(st);
-#endif
-        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
-        attention_fwd_v6<<<grid, AT6_THREADS, AT6_SMEM_BYTES, st>>>(tmQKV, ap);
     } else if (attention_variant() == 5) {
         Attn5Params ap;
         ap.n_tok = n_tok;
@@ -382,21 +345,6 @@ static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n
 #endif
         const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
         attention_fwd_v5<<<grid, AT5_THREADS, AT5_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 4) {
-        Attn4Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        ap.trace = nullptr;
-#ifdef AT4_TRACE
-        ap.trace = attention_trace_buffer(st);
-#endif
-        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
-        attention_fwd_v4<<<grid, AT4_THREADS, AT4_SMEM_BYTES, st>>>(tmQKV, ap);
     } else {
         Attn3Params ap;
         ap.n_tok = n_tok;
