@@ -56,7 +56,7 @@ __global__ void prefix_tokens_kernel(float *__restrict__ X, const float *__restr
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the hidden dimension, one warp per token (arithmetic in ln_row.cuh).
-template <bool OUT_HALF>
+template <bool OUT_HALF, int NV4 = LN_MAX_V4>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
                  void *__restrict__ out, int rows, int D, float eps) {
@@ -65,7 +65,7 @@ layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, c
     if (warp >= rows) return;
     const size_t off = static_cast<size_t>(warp) * D;
     void *orow = OUT_HALF ? static_cast<void *>(reinterpret_cast<__half *>(out) + off) : static_cast<void *>(reinterpret_cast<float *>(out) + off);
-    layernorm_row<OUT_HALF, false>(X + off, gamma, beta, orow, D, eps, lane);
+    layernorm_row<OUT_HALF, false, NV4>(X + off, gamma, beta, orow, D, eps, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

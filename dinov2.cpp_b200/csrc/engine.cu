@@ -371,8 +371,19 @@ static void launch_layernorm(const float *X, const float *g, const float *b, voi
                              cudaStream_t st) {
     if (D % 4 || D > 128 * LN_MAX_V4) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "layernorm: hidden size not supported");
     const int grid = (rows + 7) / 8;
-    if (half_out) layernorm_kernel<true><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);
-    else layernorm_kernel<false><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);
+    const int nv4 = (D + 127) / 128;          // float4 per lane; the row buffer is sized for the model width
+#define DINO_LN_CASE(n)                                                                                       \
+    if (nv4 <= n) {                                                                                            \
+        if (half_out) layernorm_kernel<true, n><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);             \
+        else layernorm_kernel<false, n><<<grid, 256, 0, st>>>(X, g, b, out, rows, D, eps);                     \
+        DINO_CUDA(cudaGetLastError());                                                                         \
+        return;                                                                                                \
+    }
+    DINO_LN_CASE(3)      // D <= 384  (ViT-S)
+    DINO_LN_CASE(6)      // D <= 768  (ViT-B)
+    DINO_LN_CASE(8)      // D <= 1024 (ViT-L)
+    DINO_LN_CASE(12)     // D <= 1536 (ViT-g)
+#undef DINO_LN_CASE
     DINO_CUDA(cudaGetLastError());
 }
 

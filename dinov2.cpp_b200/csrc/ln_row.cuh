@@ -10,15 +10,17 @@ namespace dino {
 
 constexpr int LN_MAX_V4 = 12;   // D up to 32 * 4 * 12 = 1536
 
-template <bool OUT_HALF, bool L2_ONLY>
+// NV4 = float4 per lane the row buffer is sized for (D <= 128 * NV4): sizing it to the model width instead of the maximum
+// frees registers -> more rows in flight per SM (the kernel is latency-bound per row: load, two shuffle reductions, store).
+template <bool OUT_HALF, bool L2_ONLY, int NV4 = LN_MAX_V4>
 __device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, const float *__restrict__ gamma,
                                               const float *__restrict__ beta, void *__restrict__ orow, int D, float eps, int lane) {
     const int nv = D >> 2;   // float4 per row
     const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-    float4 v[LN_MAX_V4];
+    float4 v[NV4];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
         const int idx = lane + 32 * i;
         if (idx < nv) {
             v[i] = L2_ONLY ? __ldcg(x4 + idx) : x4[idx];
@@ -30,7 +32,7 @@ __device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, co
     const float mean = sum / static_cast<float>(D);
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
         const int idx = lane + 32 * i;
         if (idx < nv) {
             v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
@@ -43,7 +45,7 @@ __device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, co
     const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
     const float4 *b4 = reinterpret_cast<const float4 *>(beta);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
         const int idx = lane + 32 * i;
         if (idx < nv) {
             const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);

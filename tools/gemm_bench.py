@@ -10,8 +10,10 @@ from dinov2_b200 import engine as E
 if len(sys.argv) > 1:
     E.LIB_PATH = os.path.abspath(sys.argv[1])
 torch.manual_seed(0)
-M = 64 * 1370
-shapes = [("qkv", E.EPI_BIAS_F16, 3072, 1024), ("proj", E.EPI_RESID_F32, 1024, 1024), ("fc1", E.EPI_GELU_F16, 4096, 1024), ("fc2", E.EPI_RESID_F32, 1024, 4096)]
+# GEMM_D / GEMM_ROWS select another model width / row count (default: ViT-L, batch 64): e.g. GEMM_D=384 GEMM_ROWS=43968 for ViT-S b32
+Dm = int(os.environ.get("GEMM_D", "1024"))
+M = int(os.environ.get("GEMM_ROWS", str(64 * 1370)))
+shapes = [("qkv", E.EPI_BIAS_F16, 3 * Dm, Dm), ("proj", E.EPI_RESID_F32, Dm, Dm), ("fc1", E.EPI_GELU_F16, 4 * Dm, Dm), ("fc2", E.EPI_RESID_F32, Dm, 4 * Dm)]
 tag = f"sms={os.environ.get('DINO_B200_GEMM_SMS','all')} cg={os.environ.get('DINO_B200_GEMM_CG','2')} mc={os.environ.get('DINO_B200_GEMM_MC','0')} lib={os.path.basename(E.LIB_PATH)}"
 for name, epi, N, K in shapes:
     A = (torch.randn(M, K, device="cuda") * 0.5).half()
