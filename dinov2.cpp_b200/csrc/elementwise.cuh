@@ -13,32 +13,40 @@ namespace dino {
 // zero-padded from 588 to `kpad` columns so the GEMM's 64-wide K boxes need no tail handling.
 // Input either RGB planar [B,3,H,W] (layout 0, what the reference uploads, dinov2.cpp:914-933) or the
 // cv::Mat layout [B,H,W,3] BGR-interleaved (layout 1) so the host never has to transpose.
-// One thread produces one (patch, channel, ky) run of `ps` contiguous kx values.
+// One thread per input PIXEL (consecutive threads read consecutive pixels: fully coalesced loads of the 3.2 MB / image that
+// dominate the traffic; the 2-byte stores of 14 neighbouring threads form one contiguous 28-byte run per channel).  Pixels
+// outside the patch grid (H or W not a multiple of ps never reaches here) do not exist; the zero pad columns 588..kpad-1 of
+// every patch row are written by the threads of the patch's first pixel row.
 __global__ void im2col_patch14_kernel(const float *__restrict__ img, __half *__restrict__ A, int B, int H, int W, int ps,
                                       int gh, int gw, int kpad, int layout) {
-    const int runs_per_patch = 3 * ps;
-    const long long total = static_cast<long long>(B) * gh * gw * (runs_per_patch + 1);   // +1: the zero pad run
+    const int HH = gh * ps, WW = gw * ps;                      // the part of the image covered by patches
+    const long long total = static_cast<long long>(B) * HH * WW;
+    const int kreal = 3 * ps * ps;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int run = static_cast<int>(idx % (runs_per_patch + 1));
-        const long long patch = idx / (runs_per_patch + 1);
-        __half *dst = A + patch * kpad;
-        if (run == runs_per_patch) {
-            for (int k = 3 * ps * ps; k < kpad; ++k) dst[k] = __float2half_rn(0.f);
-            continue;
+        const int px = static_cast<int>(idx % WW);
+        const int py = static_cast<int>((idx / WW) % HH);
+        const int b = static_cast<int>(idx / (static_cast<long long>(WW) * HH));
+        const int x = px / ps, kx = px - x * ps, y = py / ps, ky = py - y * ps;
+        __half *dst = A + (static_cast<long long>(b) * gh * gw + static_cast<long long>(y) * gw + x) * kpad + ky * ps + kx;
+        float r, g, bl;
+        if (layout == 0) {                                     // RGB planar [B,3,H,W]
+            const float *src = img + (static_cast<size_t>(b) * 3 * H + py) * W + px;
+            r = __ldg(src);
+            g = __ldg(src + static_cast<size_t>(H) * W);
+            bl = __ldg(src + 2 * static_cast<size_t>(H) * W);
+        } else {                                               // cv::Mat [B,H,W,3], BGR
+            const float *src = img + ((static_cast<size_t>(b) * H + py) * W + px) * 3;
+            bl = __ldg(src);
+            g = __ldg(src + 1);
+            r = __ldg(src + 2);
         }
-        const int c = run / ps, ky = run % ps;
-        const int x = static_cast<int>(patch % gw);
-        const int y = static_cast<int>((patch / gw) % gh);
-        const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
-        const int py = y * ps + ky, px = x * ps;
-        dst += c * ps * ps + ky * ps;
-        if (layout == 0) {
-            const float *src = img + ((static_cast<size_t>(b) * 3 + c) * H + py) * W + px;
-            for (int kx = 0; kx < ps; ++kx) dst[kx] = __float2half_rn(__ldg(src + kx));
-        } else {
-            const float *src = img + ((static_cast<size_t>(b) * H + py) * W + px) * 3 + (2 - c);   // BGR -> RGB
-            for (int kx = 0; kx < ps; ++kx) dst[kx] = __float2half_rn(__ldg(src + 3 * kx));
+        dst[0] = __float2half_rn(r);
+        dst[ps * ps] = __float2half_rn(g);
+        dst[2 * ps * ps] = __float2half_rn(bl);
+        if (ky == 0) {                                         // this patch's share of the zero padding: kx-th slice of the pad columns
+            __half *pad = dst - kx + kreal;                    // = row start + kreal
+            for (int k = kx; k < kpad - kreal; k += ps) pad[k] = __float2half_rn(0.f);
         }
     }
 }

@@ -781,7 +781,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
     // 1. patch embedding: im2col -> GEMM (+bias +pos, scattered to token rows) ; cls/register rows
     prof.begin(2);
     {
-        const long long total = static_cast<long long>(Mp) * (3 * ps + 1);
+        const long long total = static_cast<long long>(B) * (gh * ps) * (gw * ps);   // one thread per covered pixel
         const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(g_num_sms) * 16));
         im2col_patch14_kernel<<<grid, 256, 0, st>>>(images, e->Ape, B, H, W, ps, gh, gw, e->patch.ldw, layout);
         DINO_CUDA(cudaGetLastError());
