@@ -11,12 +11,12 @@
 // whatever a warp cannot hide itself is time the MUFU pipe idles, see the v5 cycle trace).  The price is that the first
 // chunk is exponentiated before the rest of the tile has been looked at: if the other 96 keys push a row more than 2^8
 // above the reference maximum, the warp rescales O_t, the sums and the 16 packed P columns already written (rare path;
-// helper shared with attention7.cuh).  v7's deeper software pipeline (loads across tile boundaries) measured slower.
+// helper shared with attention_softmax.cuh).  v7's deeper software pipeline (loads across tile boundaries) measured slower.
 //
 // Roles / TMEM map / barriers: see attention5.cuh.
 #pragma once
 #include "ptx.cuh"
-#include "attention7.cuh"   // chunk helpers: attn7_rowmax32 / attn7_mask32 / attn7_exp_pairs / attn7_rescale
+#include "attention_softmax.cuh"   // chunk helpers: attn_rowmax32 / attn_mask32 / attn_exp_pairs / attn_rescale
 
 // every AT8_POLY_MOD-th pair of probabilities is computed with a polynomial on the FMA pipe instead of MUFU (0 = none)
 #ifndef AT8_POLY_MOD
@@ -295,10 +295,10 @@ attention_fwd_v8(const __grid_constant__ CUtensorMap tmQKV, const Attn8Params p)
                 tmem_ld_32x32b_x32(hi + 32, c3);
                 AT8_SEV(12);
                 const int kv_valid = p.n_tok - j * 128;
-                if (kv_valid < 32) attn7_mask32(c0, kv_valid);
+                if (kv_valid < 32) attn_mask32(c0, kv_valid);
                 // reference maximum for chunk 0: moves only when a row grew by more than 2^8 (then O_t and the running sum
                 // are rescaled) — probabilities stay <= 256, exact in fp16
-                const float mx0 = attn7_rowmax32(c0);
+                const float mx0 = attn_rowmax32(c0);
                 if (j == 0) {
                     m_used = mx0;                         // O_t is overwritten by the first P V of the item
                     l_run = 0.f;
@@ -310,7 +310,7 @@ attention_fwd_v8(const __grid_constant__ CUtensorMap tmQKV, const Attn8Params p)
                         const float alpha = grow ? ex2_approx((m_used - mx0) * c) : 1.0f;
                         if (grow) m_used = mx0;
                         l_run *= alpha;
-                        attn7_rescale(o_addr, lo, alpha, true, 0);
+                        attn_rescale(o_addr, lo, alpha, true, 0);
                     }
                 }
                 AT8_SEV(14);
@@ -318,18 +318,18 @@ attention_fwd_v8(const __grid_constant__ CUtensorMap tmQKV, const Attn8Params p)
                 uint32_t pk[16];
                 {
                     const float mc = m_used * c;
-                    attn7_exp_pairs<0, 8>(c0, pk, c, mc, ls);
+                    attn_exp_pairs<0, 8>(c0, pk, c, mc, ls);
                     // chunks 1-3 are in registers: S(n)'s second slot may be overwritten -> the MMA warp starts S(n+1)
                     tmem_ld_wait();
                     tc_fence_before();
                     mbar_arrive(&s_free[t]);
                     if (kv_valid < 128) {
-                        attn7_mask32(c1, kv_valid - 32);
-                        attn7_mask32(c2, kv_valid - 64);
-                        attn7_mask32(c3, kv_valid - 96);
+                        attn_mask32(c1, kv_valid - 32);
+                        attn_mask32(c2, kv_valid - 64);
+                        attn_mask32(c3, kv_valid - 96);
                     }
-                    const float mx123 = fmax3(attn7_rowmax32(c1), attn7_rowmax32(c2), attn7_rowmax32(c3));
-                    attn7_exp_pairs<8, 16>(c0, pk, c, mc, ls);
+                    const float mx123 = fmax3(attn_rowmax32(c1), attn_rowmax32(c2), attn_rowmax32(c3));
+                    attn_exp_pairs<8, 16>(c0, pk, c, mc, ls);
                     tmem_st_32x32b_x16(lo, pk);
                     const bool grow = mx123 > m_used + thr;
                     if (__any_sync(0xffffffffu, grow)) {  // rare: O_t, the sums and the 16 columns of P(n) already written move down
@@ -342,16 +342,16 @@ attention_fwd_v8(const __grid_constant__ CUtensorMap tmQKV, const Attn8Params p)
                         l_run *= alpha;
                         ls[0] *= alpha;
                         ls[1] *= alpha;
-                        attn7_rescale(o_addr, lo, alpha, j > 0, 16);
+                        attn_rescale(o_addr, lo, alpha, j > 0, 16);
                     }
                 }
                 {
                     const float mc = m_used * c;
-                    attn7_exp_pairs<0, 16>(c1, pk, c, mc, ls);
+                    attn_exp_pairs<0, 16>(c1, pk, c, mc, ls);
                     tmem_st_32x32b_x16(lo + 16, pk);
-                    attn7_exp_pairs<0, 16>(c2, pk, c, mc, ls);
+                    attn_exp_pairs<0, 16>(c2, pk, c, mc, ls);
                     tmem_st_32x32b_x16(lo + 32, pk);
-                    attn7_exp_pairs<0, 16>(c3, pk, c, mc, ls);
+                    attn_exp_pairs<0, 16>(c3, pk, c, mc, ls);
                     tmem_st_32x32b_x16(lo + 48, pk);
                 }
                 l_run += ls[0] + ls[1];

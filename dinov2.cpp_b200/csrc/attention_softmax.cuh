@@ -1,0 +1,143 @@
+// Per-row softmax arithmetic shared by the TMEM-ring attention kernels (attention7.cuh, attention8.cuh): 32-key chunk
+// helpers (row maximum, masking of non-existent keys, exponentiation + row sum + fp16 packing) and the rare-path rescale
+// of O / P in tensor memory.  Semantics: reference soft_max_ext over scaled scores (dinov2.cpp:527-543, ops.cpp:4641-4737),
+// evaluated as exp2((s - m) * log2(e)/8) with a lazily updated reference maximum m.
+#pragma once
+#include "ptx.cuh"
+
+// every ATS_POLY_MOD-th pair of probabilities is computed with a polynomial on the FMA pipe instead of MUFU (0 = none)
+#ifndef ATS_POLY_MOD
+#define ATS_POLY_MOD 0   // polynomial exp2 on the FMA pipe: no gain once the softmax loop uses packed fp32 pairs (see ATS_PACKED)
+#endif
+
+namespace dino {
+
+// exp2(x) without the MUFU unit: round-to-nearest split x = n + f (magic-number add), cubic minimax for 2^f on
+// [-0.5, 0.5], exponent field patched by integer add.  Arguments below -30 (masked keys are -inf) clamp to 2^-30, which
+// is zero once P is rounded to fp16.
+__device__ __forceinline__ float attn_exp2_poly3(float x) {
+    const float t = fmaxf(x, -30.0f);
+    const float u = t + 12582912.0f;                 // 1.5 * 2^23: low mantissa bits now hold round(t)
+    const float f = t - (u - 12582912.0f);
+    float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+    p = fmaf(p, f, 0.6932762265205383f);
+    p = fmaf(p, f, 0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(u) << 23));
+}
+
+// Rare path of the lazy running-max correction: scale this thread's row of O_t (64 fp32 columns) in TMEM and, when the
+// growth was found in the middle of a tile, the first p_cols packed columns of P it has already written.  Inlined and
+// rolled (8 columns at a time): a call here would make ptxas save the 64-128 live score registers on EVERY tile.
+__device__ __forceinline__ void attn_rescale(uint32_t o_addr, uint32_t p_addr, float alpha, bool do_o, int p_cols) {
+    tmem_st_wait();                                       // this thread's earlier P stores have landed
+    if (do_o) {
+#pragma unroll 1
+        for (int i = 0; i < 64; i += 8) {
+            uint32_t a[8];
+            tmem_ld_32x32b_x8(o_addr + i, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 8; ++d) a[d] = __float_as_uint(__uint_as_float(a[d]) * alpha);
+            tmem_st_32x32b_x8(o_addr + i, a);
+        }
+    }
+    if (p_cols > 0) {
+        const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll 1
+        for (int i = 0; i < p_cols; i += 8) {
+            uint32_t q[8];
+            tmem_ld_32x32b_x8(p_addr + i, q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                __half2 v = *reinterpret_cast<__half2 *>(&q[d]);
+                v = __hmul2(v, a2);
+                q[d] = *reinterpret_cast<uint32_t *>(&v);
+            }
+            tmem_st_32x32b_x8(p_addr + i, q);
+        }
+    }
+    tmem_st_wait();
+}
+
+__device__ __forceinline__ float attn_rowmax32(const uint32_t (&v)[32]) {
+    float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+#pragma unroll
+    for (int i = 6; i < 30; i += 4) {
+        m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    }
+    return fmax3(fmax3(m0, __uint_as_float(v[30]), __uint_as_float(v[31])), m1, m1);
+}
+// keys at or beyond `valid` (relative to the chunk) do not exist: -inf
+__device__ __forceinline__ void attn_mask32(uint32_t (&v)[32], int valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i >= valid) v[i] = 0xFF800000u;
+}
+// pairs [E0, E1) of a 32-key chunk: p = exp2(s c - mc) (MUFU, every ATS_POLY_MOD-th pair on the FMA pipe), fp32 row sum,
+// one rounding to packed fp16.  ATS_PACKED: the scale-and-shift, the row sum and the polynomial run on packed fp32 pairs
+// (FFMA2 / FADD2: one issue slot per two keys).
+#ifndef ATS_PACKED
+#define ATS_PACKED 1   // measured on v8, per ViT-L layer (B=64): scalar 769 us; packed 724 us; packed + 1/4 polynomial 725, 1/3 761, 1/2 768
+#endif
+template <int E0, int E1>
+__device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2]) {
+#if ATS_PACKED
+    const f32x2 c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+    f32x2 acc = pack_f32x2(ls[0], ls[1]);
+#pragma unroll
+    for (int e = E0; e < E1; ++e) {
+        const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, nmc2);
+        float p0, p1;
+        if (ATS_POLY_MOD > 0 && (e % (ATS_POLY_MOD > 0 ? ATS_POLY_MOD : 1)) == ATS_POLY_MOD - 1) {
+            // exp2 on the FMA pipe, two keys per instruction: clamp, round-to-nearest split x = n + f (magic-number add), cubic
+            // for 2^f on [-0.5, 0.5], exponent patched in with one LEA per key
+            float x0, x1;
+            unpack_f32x2(x, x0, x1);
+            const f32x2 t = pack_f32x2(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
+            const f32x2 magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+            const f32x2 u = add2_f32(t, magic);
+            const f32x2 w = add2_f32(u, nmagic);
+            float w0, w1;
+            unpack_f32x2(w, w0, w1);
+            const f32x2 f = add2_f32(t, pack_f32x2(-w0, -w1));
+            f32x2 q = fma2_f32(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+            q = fma2_f32(q, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+            q = fma2_f32(q, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+            float q0, q1, u0, u1;
+            unpack_f32x2(q, q0, q1);
+            unpack_f32x2(u, u0, u1);
+            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(u0) << 23));
+            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(u1) << 23));
+        } else {
+            float x0, x1;
+            unpack_f32x2(x, x0, x1);
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+        }
+        acc = add2_f32(acc, pack_f32x2(p0, p1));
+        pk[e] = cvt_f16x2(p0, p1);
+    }
+    unpack_f32x2(acc, ls[0], ls[1]);
+#else
+#pragma unroll
+    for (int e = E0; e < E1; ++e) {
+        const float x0 = fmaf(__uint_as_float(v[2 * e]), c, -mc);
+        const float x1 = fmaf(__uint_as_float(v[2 * e + 1]), c, -mc);
+        float p0, p1;
+        if (ATS_POLY_MOD > 0 && (e % (ATS_POLY_MOD > 0 ? ATS_POLY_MOD : 1)) == ATS_POLY_MOD - 1) {
+            p0 = attn_exp2_poly3(x0);
+            p1 = attn_exp2_poly3(x1);
+        } else {
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+        }
+        ls[e & 1] += p0 + p1;
+        pk[e] = cvt_f16x2(p0, p1);
+    }
+#endif
+}
+
+}  // namespace dino

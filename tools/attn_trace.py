@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Cycle trace of attention v3 (CTA 0): needs lib/libdinov2_b200_trace.so (nvcc ... -DAT3_TRACE)."""
+"""Cycle trace of the attention kernel (CTA 0).  Needs a trace build of the library next to the normal one:
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -shared -DAT8_TRACE \\
+         dinov2.cpp_b200/csrc/engine.cu -o dinov2.cpp_b200/lib/libdinov2_b200_trace.so
+(-DAT3_TRACE / -DAT5_TRACE / -DAT7_TRACE with DINO_B200_ATTN=3/5/7 for the older generations).  Output: profiles/r01_attn_v*_cycle_trace.txt."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
