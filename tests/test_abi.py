@@ -55,3 +55,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "restate" not in txt and "oracle/" not in txt.replace("oracle/Makefile", "").replace("oracle/_ref", "") or f == "core.hpp", f
+
+
+def test_malformed_checkpoints_are_reported_before_any_device_work(tmp_path):
+    """The engine's own GGUF reader (csrc/gguf_reader.hpp) rejects bad files with the documented status codes — on any
+    machine, because the file is parsed before a device is required (reference: gguf_init_from_file failing in
+    dino_model_load, dinov2.cpp:263-270)."""
+    good = open(os.path.join(ROOT, "tests", "golden", "tiny_f16.gguf"), "rb").read()
+    cases = {
+        "missing.gguf": (None, 2),                                   # DINO_B200_ERR_IO
+        "bad_magic.gguf": (b"GGML" + good[4:], 3),                    # DINO_B200_ERR_FORMAT
+        "truncated_meta.gguf": (good[:200], 3),
+        "truncated_data.gguf": (good[: len(good) // 2], 3),
+        "bad_version.gguf": (good[:4] + (99).to_bytes(4, "little") + good[8:], 3),
+    }
+    for name, (blob, want) in cases.items():
+        path = tmp_path / name
+        if blob is not None:
+            path.write_bytes(blob)
+        with pytest.raises(d.DinoB200Error) as ei:
+            d.Engine(str(path))
+        assert ei.value.status == want, (name, ei.value.status, str(ei.value))
+        assert str(ei.value)                                          # a message, not just a code
