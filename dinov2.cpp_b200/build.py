@@ -33,7 +33,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for s in _sources():
         with open(s, "rb") as f:
-            h.update(s.encode() + b"\0" + f.read())
+            h.update(os.path.basename(s).encode() + b"\0" + f.read())   # names, not absolute paths: the tree is relocated on the GPU box
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
