@@ -1,0 +1,514 @@
+// Fused multi-head self-attention, generation 10: v8's tile loop, run as ONE CONTINUOUS STREAM of key tiles across work items.
+// Semantics: reference soft_max_ext(K Q^T / 8) V per head (dinov2.cpp:527-543, ops.cpp:4641-4737); fp16 operands, fp32
+// accumulation, exp2 with a lazily updated reference maximum (attention_softmax.cuh).
+//
+// What the round-2 ncu source page + cycle trace of v8 showed (profiles/r02_ncu_attn.md): inside an item the softmax
+// warps run at ~2900 cycles per 128-key tile, but every item boundary (each 11 tiles at 518 px) costs another ~4300 cycles:
+//   * the epilogue waits for the last P V, then every thread writes its 128-byte output row with 8 STG.128 whose 32 lanes
+//     hit 32 different lines (256 single-sector wavefronts per warp and item),
+//   * only then is the next item's first S = Q K^T waited for, which the MMA warp could not issue earlier (one Q buffer),
+//   * the item decode does two integer divisions per role.
+// v10 removes the boundary from the MUFU stream:
+//   1. Q is double-buffered; the MMA warp issues the NEXT item's first S while the current item's last tile is being
+//      exponentiated (the tile loop of all three roles just keeps going: stage ring, TMEM ring and barrier phases never reset),
+//   2. the epilogue of item i is deferred into the first tile of item i+1 (after its second chunk, when 64 score registers
+//      are free): O_t is only overwritten by that tile's P V, which is issued after the warpgroup has arrived on p_full,
+//   3. the output tile goes through a 128B-swizzled shared-memory staging tile and ONE TMA store per warpgroup and item
+//      (3-D tensor map [image, token, channel]: rows past the image's last token are clipped by the hardware),
+//   4. items are decoded incrementally (no divisions after the first).
+//
+//   5. ONE MMA-ISSUING WARP PER QUERY TILE (warps 11 and 10).  The ncu source page of v8 shows its single issuer busy for ~70 %
+//      of every tile period (~350 instructions: barrier-wait loops, elect / reconverge, descriptor arithmetic on the uniform
+//      datapath, 24-32 tcgen05.mma, 6 commits), and strictly in order S0, S1, PV0, PV1: the next S of tile 0 queued behind
+//      the P V of tile 1, and the softmax warps spun ~350 cycles per tile on s_full.  The hazards of the TMEM ring are per
+//      query tile, so each warp's in-order tcgen05 pipeline still covers them; shared K/V stages and Q buffers are released
+//      by barriers that count both warps.
+//
+// Roles (384 threads): warps 0-3 / 4-7 softmax warpgroups (query tile 0 / 1, one thread per row), warp 8 TMEM allocator,
+// warp 9 TMA producer, warps 11 / 10 MMA issuers of query tile 0 / 1.  TMEM: per query tile a ring of three 64-column slots (S(n) in slots n%3,
+// (n+1)%3; P(n) written back over slot n%3 as the TMEM A operand of P V) at columns 192 t, O_t at columns 384 + 64 t.
+#pragma once
+#include "ptx.cuh"
+#include "attention_softmax.cuh"   // chunk helpers: attn_rowmax32 / attn_mask32 / attn_exp_pairs / attn_rescale
+
+namespace dino {
+
+constexpr int AT10_THREADS = 384;
+constexpr int AT10_TILE = 128 * 64 * 2;          // 16 KB: a 128 x 64 fp16 tile
+#ifndef AT10_KV_STAGES
+#define AT10_KV_STAGES 4
+#endif
+#ifndef AT10_STAGGER
+#define AT10_STAGGER 0
+#endif
+// Q: 2 buffers x 2 tiles; K, V: stages; O staging: 2 tiles; barriers; alignment slack
+constexpr int AT10_SMEM_BYTES = 4 * AT10_TILE + AT10_KV_STAGES * 2 * AT10_TILE + 2 * AT10_TILE + 256 + 1024;
+constexpr float AT10_RESCALE_LOG2 = 8.0f;        // lazy-rescale threshold in the exp2 domain
+
+// Optional cycle trace of CTA 0 (compile with -DAT10_TRACE): (event id, index, clock) per role, written to p.trace
+// ([role][512][2] uint64).  Roles: 0 = MMA warp, 1 = softmax WG0 thread 0, 2 = softmax WG1 thread 0.
+#ifdef AT10_TRACE
+#define AT10_EV(ROLE, ID, IDX)                                                                 \
+    do {                                                                                       \
+        if (blockIdx.x == 0 && p.trace && tr_n < 512) {                                        \
+            p.trace[((ROLE) * 512 + tr_n) * 2] = (static_cast<unsigned long long>(ID) << 32) | static_cast<unsigned>(IDX); \
+            p.trace[((ROLE) * 512 + tr_n) * 2 + 1] = clock64();                                \
+            ++tr_n;                                                                            \
+        }                                                                                      \
+    } while (0)
+#else
+#define AT10_EV(ROLE, ID, IDX) do {} while (0)
+#endif
+
+// -DAT10_PROF: CTA 0 accumulates the cycles its roles spend in each class of barrier wait (two clock reads per wait) and
+// writes them to p.trace: [0] producer kv_empty, [1] producer q_empty, [2] MMA0 kv_full, [3] MMA0 s_free, [4] MMA0 p_full,
+// [5] MMA0 q_full, [6] WG0 s_full, [7] WG0 o_full (epilogue), [8] WG0 total, [9] MMA0 total, [10] WG0 epilogue total.
+#ifdef AT10_PROF
+#define AT10_PWAIT(SLOT, STMT)                                        \
+    do {                                                              \
+        const long long t0__ = clock64();                             \
+        STMT;                                                         \
+        prof_acc[SLOT] += clock64() - t0__;                           \
+    } while (0)
+#else
+#define AT10_PWAIT(SLOT, STMT) do { STMT; } while (0)
+#endif
+
+struct Attn10Params {
+    int n_tok;
+    int hidden;
+    int n_heads;
+    int n_qblk;        // ceil(n_tok / 256)
+    int num_items;     // batch * n_heads * n_qblk
+    __half *out;       // (unused by the kernel: the output is written through tmOut)
+    float scale_log2;  // log2(e) / sqrt(64)
+    unsigned long long *trace;   // AT10_TRACE builds only
+};
+
+// 3-D tiled store shared -> global; parts of the box outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// Work item -> (image, head, query block), walked incrementally: consecutive items share K/V (same image and head).
+struct Attn10Item {
+    int qb, head, img;
+    __device__ __forceinline__ void init(int item, int n_qblk, int n_heads) {
+        qb = item % n_qblk;
+        const int ih = item / n_qblk;
+        head = ih % n_heads;
+        img = ih / n_heads;
+    }
+    __device__ __forceinline__ void next(int n_qblk, int n_heads) {
+        if (++qb == n_qblk) {
+            qb = 0;
+            if (++head == n_heads) {
+                head = 0;
+                ++img;
+            }
+        }
+    }
+    __device__ __forceinline__ bool has_q1(int n_tok) const { return qb * 256 + 128 < n_tok; }
+};
+
+__global__ void __launch_bounds__(AT10_THREADS, 1)
+attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, const Attn10Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem;                                   // [buffer][tile]
+    uint8_t *sK = sQ + 4 * AT10_TILE;                     // [stages]
+    uint8_t *sV = sK + AT10_KV_STAGES * AT10_TILE;        // [stages]
+    uint8_t *sO = sV + AT10_KV_STAGES * AT10_TILE;        // [tile]: output staging
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sO + 2 * AT10_TILE);
+    uint64_t *q_full = bars;                              // 2
+    uint64_t *q_empty = bars + 2;                         // 2
+    uint64_t *kv_full = bars + 4;                         // stages
+    uint64_t *kv_empty = kv_full + AT10_KV_STAGES;        // stages
+    uint64_t *s_full = kv_empty + AT10_KV_STAGES;         // 2: S_t(n) is in TMEM
+    uint64_t *s_free = s_full + 2;                        // 2: S_t(n) is in registers (its second slot may be overwritten)
+    // P_t(n) is in TMEM.  Two barriers per tile, used alternately: a warpgroup may finish P_t(n+1) before the MMA warp (held
+    // up by the other tile) has looked at P_t(n) — with a single barrier that is two phase flips and the parity wait never
+    // returns.  It cannot be two tiles ahead: S_t(n+2) is only issued after the MMA warp has consumed P_t(n).
+    uint64_t *p_full = s_free + 2;                        // 2 x 2
+    uint64_t *o_full = p_full + 4;                        // 2: P_t(n) V has completed
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_kv = (p.n_tok + 127) / 128;
+    // contiguous, balanced item range of this CTA: consecutive items share K/V (same image and head), so a CTA re-reads
+    // them from L2, and every CTA gets the same mix of full and half (single query tile) blocks
+    const int item_lo = static_cast<int>(static_cast<long long>(p.num_items) * blockIdx.x / gridDim.x);
+    const int item_hi = static_cast<int>(static_cast<long long>(p.num_items) * (blockIdx.x + 1) / gridDim.x);
+
+#ifdef AT10_PROF
+    long long prof_acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
+    if (warp == 9 && lane == 0) {
+        prefetch_tmap(&tmQKV);
+        prefetch_tmap(&tmOut);
+    }
+    if (warp == 11 && lane == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&q_full[b], 1);
+            mbar_init(&q_empty[b], 2);                    // both MMA warps have issued their last Q K^T of the item
+        }
+        for (int s = 0; s < AT10_KV_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 2);                   // both MMA warps' P V products that read the stage have completed
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 128);
+            mbar_init(&p_full[2 * t], 128);
+            mbar_init(&p_full[2 * t + 1], 128);
+            mbar_init(&o_full[t], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_R = tmem_base;           // ring of tile t: columns 192 t + 64 slot
+    const uint32_t tmem_O = tmem_base + 384;     // O_t at columns 384 + 64 t
+
+    if (warp >= 8) {
+        setmaxnreg_dec<80>();
+        if (warp == 9 && item_lo < item_hi) {
+            // ---------------------------------------------------------------- TMA producer (warp-uniform; one lane issues)
+            int s = 0;
+            uint32_t ph = 0, li = 0;                       // K/V stage + phase; local item index (Q buffer = li & 1)
+            Attn10Item it;
+            it.init(item_lo, p.n_qblk, p.n_heads);
+            for (int item = item_lo; item < item_hi; ++item, ++li, it.next(p.n_qblk, p.n_heads)) {
+                const int row_base = it.img * p.n_tok, q_base = it.qb * 256;
+                const bool has_q1 = it.has_q1(p.n_tok);
+                const uint32_t qb = li & 1;
+                AT10_PWAIT(1, mbar_wait(&q_empty[qb], ((li >> 1) & 1) ^ 1));   // every Q K^T of the item that used this buffer last has completed
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&q_full[qb], (has_q1 ? 2 : 1) * AT10_TILE);
+                    tma_load_2d(sQ + qb * 2 * AT10_TILE, &tmQKV, &q_full[qb], it.head * 64, row_base + q_base);
+                    if (has_q1) tma_load_2d(sQ + (qb * 2 + 1) * AT10_TILE, &tmQKV, &q_full[qb], it.head * 64, row_base + q_base + 128);
+                }
+                __syncwarp();
+                for (int j = 0; j < n_kv; ++j) {
+                    AT10_PWAIT(0, mbar_wait(&kv_empty[s], ph ^ 1));
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&kv_full[s], 2 * AT10_TILE);
+                        tma_load_2d(sK + s * AT10_TILE, &tmQKV, &kv_full[s], p.hidden + it.head * 64, row_base + j * 128);
+                        tma_load_2d(sV + s * AT10_TILE, &tmQKV, &kv_full[s], 2 * p.hidden + it.head * 64, row_base + j * 128);
+                    }
+                    __syncwarp();
+                    if (++s == AT10_KV_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp >= 10 && item_lo < item_hi) {
+            // ---------------------------------------------------------------- MMA issuers: warp 11 -> query tile 0, warp 10 -> tile 1
+            // All 32 lanes run the control flow, barrier waits and descriptor arithmetic (warp-uniform -> uniform
+            // datapath); one elected lane issues tcgen05.mma / tcgen05.commit.  Both warps walk every item and tile; the
+            // tile-1 warp skips the MMAs of items without a second query tile but still takes part in the stage / Q-buffer
+            // hand-backs (a commit with nothing outstanding arrives at once).
+            const int T = 11 - warp;
+            constexpr uint32_t idesc_s128 = make_idesc_f16(128, 128, 0, 0);
+            constexpr uint32_t idesc_s64 = make_idesc_f16(128, 64, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);     // A = P (TMEM), B = V, MN-major
+            int s = 0;                                     // K/V stage of the tile whose P V comes next
+            uint32_t ph = 0, li = 0;
+            uint32_t n_s = 0, n_p = 0;                     // S / P tiles issued so far: barrier phase = count & 1
+            uint32_t slot_s = 0, slot_p = 0;               // ring slots (count % 3) of the next S / next P
+            [[maybe_unused]] int tr_n = 0;
+            const uint32_t ring = tmem_R + T * 192;
+            const uint32_t o_acc = tmem_O + T * 64;
+            const uint64_t q_desc_base = make_smem_desc_sw128(smem_u32(sQ + T * AT10_TILE), 16, 1024);
+            const uint64_t k_desc_base = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            // MN-major B, N = 64: a single 64-wide atom along MN (leading-dim offset unused)
+            const uint64_t v_desc_base = make_smem_desc_sw128(smem_u32(sV), 1024, 1024);
+// S(n) = Q K(stage)^T into ring slots (slot, slot+1 mod 3): one N=128 MMA per k-step when the slots are adjacent,
+// two N=64 MMAs (keys 0-63 -> slot 2, keys 64-127 -> slot 0; K rows 64.. start 8 KB into the tile) when the ring wraps
+#define AT10_ISSUE_S(QDESC, STAGE)                                                                                     \
+    do {                                                                                                               \
+        if (n_s > 0) {                                                                                                 \
+            AT10_PWAIT(3, mbar_wait(&s_free[T], (n_s - 1) & 1));                                                       \
+            tc_fence_after();                                                                                          \
+        }                                                                                                              \
+        const uint64_t k_desc__ = k_desc_base + static_cast<uint64_t>((STAGE) * (AT10_TILE >> 4));                     \
+        if (elect_one()) {                                                                                             \
+            if (slot_s != 2) {                                                                                         \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                          \
+                    umma_f16_ss(ring + slot_s * 64, (QDESC) + 2 * k, k_desc__ + 2 * k, idesc_s128, k != 0);            \
+            } else {                                                                                                   \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                                        \
+                    umma_f16_ss(ring + 128, (QDESC) + 2 * k, k_desc__ + 2 * k, idesc_s64, k != 0);                     \
+                    umma_f16_ss(ring, (QDESC) + 2 * k, k_desc__ + (8192 >> 4) + 2 * k, idesc_s64, k != 0);             \
+                }                                                                                                      \
+            }                                                                                                          \
+            umma_commit(&s_full[T]);                                                                                   \
+            if (T == 0) AT10_EV(0, 1 + T, n_s);                                                                                    \
+        }                                                                                                              \
+        __syncwarp();                                                                                                  \
+        n_s++;                                                                                                         \
+        slot_s = slot_s == 2 ? 0u : slot_s + 1;                                                                        \
+    } while (0)
+            Attn10Item it;
+            it.init(item_lo, p.n_qblk, p.n_heads);
+            bool act = T == 0 || it.has_q1(p.n_tok);       // this warp's query tile exists in the current item
+            // the very first S of this CTA
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            if (act) AT10_ISSUE_S(q_desc_base, 0);
+            if (n_kv == 1 && elect_one()) umma_commit(&q_empty[0]);
+            __syncwarp();
+            for (int item = item_lo; item < item_hi; ++item, ++li) {
+                const bool has_next = item + 1 < item_hi;
+                it.next(p.n_qblk, p.n_heads);
+                const bool act_next = has_next && (T == 0 || it.has_q1(p.n_tok));
+                const uint64_t q_cur = q_desc_base + static_cast<uint64_t>((li & 1) * ((2 * AT10_TILE) >> 4));
+                const uint64_t q_nxt = q_desc_base + static_cast<uint64_t>(((li + 1) & 1) * ((2 * AT10_TILE) >> 4));
+                for (int j = 0; j < n_kv; ++j) {
+                    int s1 = s + 1;
+                    uint32_t ph1 = ph;
+                    if (s1 == AT10_KV_STAGES) { s1 = 0; ph1 ^= 1; }
+                    if (j + 1 < n_kv) {
+                        // S(j+1) of this item: computed while S(j) is being exponentiated
+                        AT10_PWAIT(2, mbar_wait(&kv_full[s1], ph1));
+                        tc_fence_after();
+                        if (T == 0) AT10_EV(0, 5, j);
+                        if (act) AT10_ISSUE_S(q_cur, s1);
+                        if (j + 2 == n_kv && elect_one()) umma_commit(&q_empty[li & 1]);   // last Q K^T of this item is in flight
+                        __syncwarp();
+                    } else if (has_next) {
+                        // first S of the NEXT item (other Q buffer): the tile stream does not stop at the item boundary
+                        AT10_PWAIT(5, mbar_wait(&q_full[(li + 1) & 1], ((li + 1) >> 1) & 1));
+                        AT10_PWAIT(2, mbar_wait(&kv_full[s1], ph1));
+                        tc_fence_after();
+                        if (T == 0) AT10_EV(0, 6, j);
+                        if (act_next) AT10_ISSUE_S(q_nxt, s1);
+                        if (n_kv == 1 && elect_one()) umma_commit(&q_empty[(li + 1) & 1]);
+                        __syncwarp();
+                    }
+                    // O (+)= P(n) V  (8 k-steps of 16 keys; P = 8 TMEM columns per step in ring slot n % 3), then o_full
+                    if (act) {
+                        AT10_PWAIT(4, mbar_wait(&p_full[2 * T + (n_p & 1)], (n_p >> 1) & 1));
+                        tc_fence_after();
+                        if (T == 0) AT10_EV(0, 7, n_p);
+                    }
+                    const uint64_t v_desc = v_desc_base + static_cast<uint64_t>(s * (AT10_TILE >> 4));
+                    if (elect_one()) {
+                        if (act) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                umma_f16_ts(o_acc, ring + slot_p * 64 + 8 * k, v_desc + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, (j | k) != 0);
+                            umma_commit(&o_full[T]);
+                            if (T == 0) AT10_EV(0, 3 + T, n_p);
+                        }
+                        umma_commit(&kv_empty[s]);         // this warp's share of the stage hand-back
+                    }
+                    __syncwarp();
+                    if (act) {
+                        n_p++;
+                        slot_p = slot_p == 2 ? 0u : slot_p + 1;
+                    }
+                    s = s1;
+                    ph = ph1;
+                }
+                act = act_next;
+            }
+        }
+    } else {
+        setmaxnreg_inc<208>();
+        const int t = warp >> 2;                          // query tile / warpgroup
+        const int qd = warp & 3;                          // TMEM lane quarter
+        const int r = qd * 32 + lane;                     // row inside the tile
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t ring = tmem_R + lane_addr + t * 192;          // this row's ring of three 64-column slots
+        const uint32_t o_addr = tmem_O + lane_addr + t * 64;
+        const float c = p.scale_log2;
+        const float thr = AT10_RESCALE_LOG2 / c;          // threshold in raw-score units
+        uint32_t n_tile = 0;                              // tiles processed by this warpgroup (barrier phases)
+        uint32_t slot = 0;                                // n_tile % 3
+        [[maybe_unused]] int tr_n = 0;
+        uint8_t *stage_row = sO + t * AT10_TILE + r * 128;           // this row of the warpgroup's output staging tile
+        const uint32_t sw = static_cast<uint32_t>(r & 7);            // 128-B swizzle: chunk c of row r lives at c ^ (r & 7)
+        const bool wg_leader = (threadIdx.x & 127) == 0;
+#define AT10_SEV(ID) do { if ((threadIdx.x & 127) == 0) AT10_EV(1 + t, ID, n_tile); } while (0)
+
+        // Deferred epilogue state: the finished item whose O_t is still in tensor memory
+        bool pending = false;
+        float pend_l = 1.f;
+        int pend_c0 = 0, pend_c1 = 0, pend_c2 = 0;        // TMA store coordinates: channel, token, image
+// O_t / rowsum -> fp16 rows -> swizzled staging tile -> one TMA store.  Runs with n_tile = index of the tile AFTER the item's last.
+#define AT10_EPILOGUE()                                                                                                \
+    do {                                                                                                               \
+        AT10_PWAIT(7, mbar_wait(&o_full[t], (n_tile - 1) & 1));                                                        \
+        tc_fence_after();                                                                                              \
+        uint32_t a__[32], b__[32];                                                                                     \
+        tmem_ld_32x32b_x32(o_addr, a__);                                                                               \
+        tmem_ld_32x32b_x32(o_addr + 32, b__);                                                                          \
+        tmem_ld_wait();                                                                                                \
+        tc_fence_before();                                                                                             \
+        if (wg_leader) bulk_wait_read<0>();      /* the previous store has finished reading the staging tile */        \
+        named_bar_sync(1 + t, 128);                                                                                    \
+        const float inv__ = 1.0f / pend_l;                                                                             \
+        _Pragma("unroll") for (int v = 0; v < 4; ++v) {                                                                \
+            *reinterpret_cast<uint4 *>(stage_row + ((static_cast<uint32_t>(v) ^ sw) << 4)) =                           \
+                make_uint4(pack_half2(__uint_as_float(a__[8 * v]) * inv__, __uint_as_float(a__[8 * v + 1]) * inv__),   \
+                           pack_half2(__uint_as_float(a__[8 * v + 2]) * inv__, __uint_as_float(a__[8 * v + 3]) * inv__), \
+                           pack_half2(__uint_as_float(a__[8 * v + 4]) * inv__, __uint_as_float(a__[8 * v + 5]) * inv__), \
+                           pack_half2(__uint_as_float(a__[8 * v + 6]) * inv__, __uint_as_float(a__[8 * v + 7]) * inv__)); \
+            *reinterpret_cast<uint4 *>(stage_row + ((static_cast<uint32_t>(v + 4) ^ sw) << 4)) =                       \
+                make_uint4(pack_half2(__uint_as_float(b__[8 * v]) * inv__, __uint_as_float(b__[8 * v + 1]) * inv__),   \
+                           pack_half2(__uint_as_float(b__[8 * v + 2]) * inv__, __uint_as_float(b__[8 * v + 3]) * inv__), \
+                           pack_half2(__uint_as_float(b__[8 * v + 4]) * inv__, __uint_as_float(b__[8 * v + 5]) * inv__), \
+                           pack_half2(__uint_as_float(b__[8 * v + 6]) * inv__, __uint_as_float(b__[8 * v + 7]) * inv__)); \
+        }                                                                                                              \
+        fence_proxy_async_smem();                                                                                      \
+        named_bar_sync(1 + t, 128);                                                                                    \
+        if (wg_leader) {                                                                                               \
+            tma_store_3d(&tmOut, sO + t * AT10_TILE, pend_c0, pend_c1, pend_c2);                                       \
+            bulk_commit();                                                                                             \
+        }                                                                                                              \
+        pending = false;                                                                                               \
+    } while (0)
+
+#if AT10_STAGGER > 0
+        // start the second warpgroup part of a tile late: with one MMA warp per query tile and no per-item resynchronisation
+        // nothing pulls the two warpgroups back into lock-step, so one of them can feed the MUFU pipe while the other waits
+        // for / loads / max-reduces its next scores
+        if (t == 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < AT10_STAGGER) {}
+        }
+#endif
+        Attn10Item it;
+        it.init(item_lo, p.n_qblk, p.n_heads);
+        for (int item = item_lo; item < item_hi; ++item, it.next(p.n_qblk, p.n_heads)) {
+            if (t == 1 && !it.has_q1(p.n_tok)) continue;
+            float m_used = -INFINITY;
+            float l_run = 0.f;                            // softmax denominator relative to m_used
+
+            for (int j = 0; j < n_kv; ++j, ++n_tile) {
+                const uint32_t lo = ring + slot * 64;                          // keys 0-63 (P goes back here)
+                const uint32_t hi = ring + (slot == 2 ? 0u : slot + 1) * 64;   // keys 64-127
+                slot = slot == 2 ? 0u : slot + 1;
+                AT10_SEV(10);
+                AT10_PWAIT(6, mbar_wait(&s_full[t], n_tile & 1));
+                tc_fence_after();
+                AT10_SEV(11);
+                uint32_t c0[32], c1[32], c2[32], c3[32];
+                tmem_ld_32x32b_x32(lo, c0);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(lo + 32, c1);          // in flight under chunk 0's maximum and first exponentials
+                tmem_ld_32x32b_x32(hi, c2);
+                tmem_ld_32x32b_x32(hi + 32, c3);
+                AT10_SEV(12);
+                const int kv_valid = p.n_tok - j * 128;
+                if (kv_valid < 32) attn_mask32(c0, kv_valid);
+                // reference maximum for chunk 0: moves only when a row grew by more than 2^8 (then O_t and the running sum
+                // are rescaled) — probabilities stay <= 256, exact in fp16
+                const float mx0 = attn_rowmax32(c0);
+                if (j == 0) {
+                    m_used = mx0;                         // O_t is overwritten by the first P V of the item
+                    l_run = 0.f;
+                } else {
+                    const bool grow = mx0 > m_used + thr;
+                    if (__any_sync(0xffffffffu, grow)) {  // rare: O_t must be quiescent, i.e. P(j-1) V(j-1) complete
+                        mbar_wait(&o_full[t], (n_tile - 1) & 1);
+                        tc_fence_after();
+                        const float alpha = grow ? ex2_approx((m_used - mx0) * c) : 1.0f;
+                        if (grow) m_used = mx0;
+                        l_run *= alpha;
+                        attn_rescale(o_addr, lo, alpha, true, 0);
+                    }
+                }
+                AT10_SEV(14);
+                float ls[2] = {0.f, 0.f};
+                uint32_t pk[16];
+                {
+                    const float mc = m_used * c;
+                    attn_exp_pairs<0, 8>(c0, pk, c, mc, ls);
+                    // chunks 1-3 are in registers: S(n)'s second slot may be overwritten -> the MMA warp starts S(n+1)
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&s_free[t]);
+                    if (kv_valid < 128) {
+                        attn_mask32(c1, kv_valid - 32);
+                        attn_mask32(c2, kv_valid - 64);
+                        attn_mask32(c3, kv_valid - 96);
+                    }
+                    const float mx123 = fmax3(attn_rowmax32(c1), attn_rowmax32(c2), attn_rowmax32(c3));
+                    attn_exp_pairs<8, 16>(c0, pk, c, mc, ls);
+                    tmem_st_32x32b_x16(lo, pk);
+                    const bool grow = mx123 > m_used + thr;
+                    if (__any_sync(0xffffffffu, grow)) {  // rare: O_t, the sums and the 16 columns of P(n) already written move down
+                        if (j > 0) {
+                            mbar_wait(&o_full[t], (n_tile - 1) & 1);
+                            tc_fence_after();
+                        }
+                        const float alpha = grow ? ex2_approx((m_used - mx123) * c) : 1.0f;
+                        if (grow) m_used = mx123;
+                        l_run *= alpha;
+                        ls[0] *= alpha;
+                        ls[1] *= alpha;
+                        attn_rescale(o_addr, lo, alpha, j > 0, 16);
+                    }
+                }
+                {
+                    const float mc = m_used * c;
+                    attn_exp_pairs<0, 16>(c1, pk, c, mc, ls);
+                    tmem_st_32x32b_x16(lo + 16, pk);
+                    // The previous item's output: O_t stays untouched until this tile's P V, which is issued only after the
+                    // p_full arrive below.  64 score registers (chunks 0 and 1) are free at this point.
+                    if (j == 0 && pending) {
+                        AT10_SEV(18);
+                        AT10_PWAIT(10, AT10_EPILOGUE());
+                        AT10_SEV(19);
+                    }
+                    attn_exp_pairs<0, 16>(c2, pk, c, mc, ls);
+                    tmem_st_32x32b_x16(lo + 32, pk);
+                    attn_exp_pairs<0, 16>(c3, pk, c, mc, ls);
+                    tmem_st_32x32b_x16(lo + 48, pk);
+                }
+                l_run += ls[0] + ls[1];
+                AT10_SEV(15);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[2 * t + (n_tile & 1)]);
+                AT10_SEV(17);
+            }
+            pending = true;
+            pend_l = l_run;
+            pend_c0 = it.head * 64;
+            pend_c1 = it.qb * 256 + t * 128;
+            pend_c2 = it.img;
+        }
+        if (pending) AT10_EPILOGUE();
+        if (wg_leader) bulk_wait<0>();                    // the staging tile must outlive the last TMA store
+    }
+
+#ifdef AT10_PROF
+    if (blockIdx.x == 0 && p.trace && lane == 0) {
+        const long long tot = clock64() - prof_t0;
+        if (warp == 9) { p.trace[0] = prof_acc[0]; p.trace[1] = prof_acc[1]; }
+        if (warp == 11) { p.trace[2] = prof_acc[2]; p.trace[3] = prof_acc[3]; p.trace[4] = prof_acc[4]; p.trace[5] = prof_acc[5]; p.trace[9] = tot; }
+        if (warp == 0) { p.trace[6] = prof_acc[6]; p.trace[7] = prof_acc[7]; p.trace[8] = tot; p.trace[10] = prof_acc[10]; }
+    }
+#endif
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+#undef AT10_SEV
+#undef AT10_ISSUE_S
+#undef AT10_EPILOGUE
+
+}  // namespace dino

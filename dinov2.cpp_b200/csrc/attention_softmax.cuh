@@ -6,8 +6,11 @@
 #include "ptx.cuh"
 
 // every ATS_POLY_MOD-th pair of probabilities is computed with a polynomial on the FMA pipe instead of MUFU (0 = none)
+// Round 2: with one MMA-issuing warp per query tile (attention10.cuh) the exponentiation phase runs the XU pipe (MUFU.EX2 at
+// 16 / clk / SM plus the F2FP packs) at ~94 %, so moving exponentials to the FMA pipe pays again.  Per ViT-L layer (B = 64) on
+// v10: 0 -> 705 us, 8 -> 697, 4 -> 675, 3 -> 666, 2 -> 694 (a polynomial pair costs ~14 issue slots against 6 for a MUFU pair).
 #ifndef ATS_POLY_MOD
-#define ATS_POLY_MOD 0   // polynomial exp2 on the FMA pipe: no gain once the softmax loop uses packed fp32 pairs (see ATS_PACKED)
+#define ATS_POLY_MOD 3
 #endif
 
 namespace dino {
@@ -82,43 +85,57 @@ __device__ __forceinline__ void attn_mask32(uint32_t (&v)[32], int valid) {
 #ifndef ATS_PACKED
 #define ATS_PACKED 1   // measured on v8, per ViT-L layer (B=64): scalar 769 us; packed 724 us; packed + 1/4 polynomial 725, 1/3 761, 1/2 768
 #endif
+// ATS_PIPE: the row-sum add and the fp16 pack of pair e are placed ATS_PIPE pairs after its two MUFU ops in program order.
+// Measured (SASS of ATS_PIPE = 1, 2, 3 is identical): ptxas re-schedules the block on its own and always pipelines by exactly
+// one pair — MUFU (stall 8), MUFU, FADD2(previous pair), F2FP(previous pair, stall 6) — whatever the source order says.
+#ifndef ATS_PIPE
+#define ATS_PIPE 1
+#endif
 template <int E0, int E1>
 __device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2]) {
 #if ATS_PACKED
     const f32x2 c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
     f32x2 acc = pack_f32x2(ls[0], ls[1]);
+    float q0[E1 - E0], q1[E1 - E0];
 #pragma unroll
-    for (int e = E0; e < E1; ++e) {
-        const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, nmc2);
-        float p0, p1;
-        if (ATS_POLY_MOD > 0 && (e % (ATS_POLY_MOD > 0 ? ATS_POLY_MOD : 1)) == ATS_POLY_MOD - 1) {
-            // exp2 on the FMA pipe, two keys per instruction: clamp, round-to-nearest split x = n + f (magic-number add), cubic
-            // for 2^f on [-0.5, 0.5], exponent patched in with one LEA per key
-            float x0, x1;
-            unpack_f32x2(x, x0, x1);
-            const f32x2 t = pack_f32x2(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
-            const f32x2 magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
-            const f32x2 u = add2_f32(t, magic);
-            const f32x2 w = add2_f32(u, nmagic);
-            float w0, w1;
-            unpack_f32x2(w, w0, w1);
-            const f32x2 f = add2_f32(t, pack_f32x2(-w0, -w1));
-            f32x2 q = fma2_f32(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
-            q = fma2_f32(q, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
-            q = fma2_f32(q, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
-            float q0, q1, u0, u1;
-            unpack_f32x2(q, q0, q1);
-            unpack_f32x2(u, u0, u1);
-            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(u0) << 23));
-            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(u1) << 23));
-        } else {
-            float x0, x1;
-            unpack_f32x2(x, x0, x1);
-            p0 = ex2_approx(x0);
-            p1 = ex2_approx(x1);
+    for (int e = E0; e < E1 + ATS_PIPE; ++e) {
+        if (e < E1) {
+            const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, nmc2);
+            float p0, p1;
+            if (ATS_POLY_MOD > 0 && (e % (ATS_POLY_MOD > 0 ? ATS_POLY_MOD : 1)) == ATS_POLY_MOD - 1) {
+                // exp2 on the FMA pipe, two keys per instruction: clamp, round-to-nearest split x = n + f (magic-number add), cubic
+                // for 2^f on [-0.5, 0.5], exponent patched in with one LEA per key
+                float x0, x1;
+                unpack_f32x2(x, x0, x1);
+                const f32x2 t = pack_f32x2(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
+                const f32x2 magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+                const f32x2 u = add2_f32(t, magic);
+                const f32x2 w = add2_f32(u, nmagic);
+                float w0, w1;
+                unpack_f32x2(w, w0, w1);
+                const f32x2 f = add2_f32(t, pack_f32x2(-w0, -w1));
+                f32x2 q = fma2_f32(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+                q = fma2_f32(q, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+                q = fma2_f32(q, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+                float r0, r1, u0, u1;
+                unpack_f32x2(q, r0, r1);
+                unpack_f32x2(u, u0, u1);
+                p0 = __int_as_float(__float_as_int(r0) + (__float_as_int(u0) << 23));
+                p1 = __int_as_float(__float_as_int(r1) + (__float_as_int(u1) << 23));
+            } else {
+                float x0, x1;
+                unpack_f32x2(x, x0, x1);
+                p0 = ex2_approx_ordered(x0);
+                p1 = ex2_approx_ordered(x1);
+            }
+            q0[e - E0] = p0;
+            q1[e - E0] = p1;
         }
-        acc = add2_f32(acc, pack_f32x2(p0, p1));
-        pk[e] = cvt_f16x2(p0, p1);
+        if (e - ATS_PIPE >= E0) {
+            const int d = e - ATS_PIPE;
+            acc = add2_f32_ordered(acc, pack_f32x2(q0[d - E0], q1[d - E0]));
+            pk[d] = cvt_f16x2(q0[d - E0], q1[d - E0]);
+        }
     }
     unpack_f32x2(acc, ls[0], ls[1]);
 #else

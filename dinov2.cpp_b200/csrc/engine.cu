@@ -6,10 +6,15 @@
 #include "../../include/dinov2_b200.h"
 
 #include "attention_common.cuh"
+// Superseded attention generations (v3, v5, v7), the weight-multicast GEMM (MC = 2) and the L2-read-back LayerNorm epilogue are
+// measurement history: they are compiled only with -DDINO_B200_EXPERIMENTAL (tools/build_experimental.sh), never into the product .so.
+#ifdef DINO_B200_EXPERIMENTAL
 #include "attention3.cuh"
 #include "attention5.cuh"
 #include "attention7.cuh"
 #include "attention8.cuh"
+#endif
+#include "attention10.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gguf_reader.hpp"
@@ -24,9 +29,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -101,6 +108,21 @@ static CUtensorMapL2promotion attn_promotion() {
     }();
     return v;
 }
+// fp16 [images, rows, cols] (row stride ld elements, image stride rows * ld): box = 64 columns x box_rows rows of ONE image, 128-B
+// swizzle.  Used for the attention output: a query tile that straddles the last token of an image is clipped per image.
+static CUtensorMap make_tmap_3d_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t images, uint64_t ld, uint32_t box_rows) {
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {cols, rows, images};
+    const cuuint64_t gstride[2] = {ld * sizeof(__half), rows * ld * sizeof(__half)};
+    const cuuint32_t box[3] = {64, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstride[0] & 15) || (gstride[1] & 15)) throw CudaError("TMA operand is not 16-byte aligned");
+    const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
 static CUtensorMap make_tmap_f16(const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
     return make_tmap_2d(ptr, false, cols, rows, ld, box_rows);
 }
@@ -110,7 +132,6 @@ static CUtensorMap make_tmap_out(int epi, const void *out, uint64_t cols, uint64
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-static int g_num_sms = 0;
 
 // DINO_B200_GEMM_CG=1 selects the one-CTA-per-tile GEMM (A/B comparisons); default: CTA pairs (cta_group::2)
 static int gemm_cg() {
@@ -121,45 +142,60 @@ static int gemm_cg() {
     return v;
 }
 
+#ifdef DINO_B200_EXPERIMENTAL
 template <int EPI> static void configure_gemm_mc() {
     DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<256, EPI, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 2>::kSmemBytes));
 }
+#endif
 template <int BN, int EPI> static void configure_gemm() {
     DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 1>::kSmemBytes));
     DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 2>::kSmemBytes));
 }
-static void configure_kernels_once() {
-    static std::once_flag once;
-    static std::string err;
-    std::call_once(once, [] {
-        try {
-            int dev = 0;
-            DINO_CUDA(cudaGetDevice(&dev));
-            DINO_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-            configure_gemm_mc<EPI_BIAS_F16>();
-            configure_gemm_mc<EPI_GELU_F16>();
-            configure_gemm_mc<EPI_RESID_F32>();
-            configure_gemm_mc<EPI_SWIGLU_F16>();
-            configure_gemm<256, EPI_BIAS_F16>();
-            configure_gemm<128, EPI_BIAS_F16>();
-            configure_gemm<256, EPI_GELU_F16>();
-            configure_gemm<128, EPI_GELU_F16>();
-            configure_gemm<256, EPI_RESID_F32>();
-            configure_gemm<128, EPI_RESID_F32>();
-            configure_gemm<256, EPI_RESID_LN_F32>();
-            configure_gemm<128, EPI_RESID_LN_F32>();
-            configure_gemm<256, EPI_SWIGLU_F16>();
-            configure_gemm<256, EPI_PATCH_F32>();
-            configure_gemm<128, EPI_PATCH_F32>();
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
-            DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM_BYTES));
-        } catch (const std::exception &e) {
-            err = e.what();
-        }
-    });
-    if (!err.empty()) throw CudaError(err);
+// Per-device state: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and SM counts may
+// differ between devices, so both are tracked per ordinal (one process may hold engines on several GPUs).
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    bool configured = false;
+    int num_sms = 0;
+};
+static std::mutex g_dev_mutex;
+static DeviceState g_dev[kMaxDevices];
+
+static void configure_current_device_locked(DeviceState &d, int dev) {
+    DINO_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+#ifdef DINO_B200_EXPERIMENTAL
+    configure_gemm_mc<EPI_BIAS_F16>();
+    configure_gemm_mc<EPI_GELU_F16>();
+    configure_gemm_mc<EPI_RESID_F32>();
+    configure_gemm_mc<EPI_SWIGLU_F16>();
+    configure_gemm<256, EPI_RESID_LN_F32>();
+    configure_gemm<128, EPI_RESID_LN_F32>();
+    DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
+    DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
+    DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
+    DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM_BYTES));
+#endif
+    configure_gemm<256, EPI_BIAS_F16>();
+    configure_gemm<128, EPI_BIAS_F16>();
+    configure_gemm<256, EPI_GELU_F16>();
+    configure_gemm<128, EPI_GELU_F16>();
+    configure_gemm<256, EPI_RESID_F32>();
+    configure_gemm<128, EPI_RESID_F32>();
+    configure_gemm<256, EPI_SWIGLU_F16>();
+    configure_gemm<256, EPI_PATCH_F32>();
+    configure_gemm<128, EPI_PATCH_F32>();
+    DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v10, cudaFuncAttributeMaxDynamicSharedMemorySize, AT10_SMEM_BYTES));
+    d.configured = true;
+}
+// Opt-in shared-memory sizes for the current device (idempotent); returns its SM count.
+static int configure_current_device() {
+    int dev = 0;
+    DINO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) throw CudaError("device ordinal out of range");
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceState &d = g_dev[dev];
+    if (!d.configured) configure_current_device_locked(d, dev);
+    return d.num_sms;
 }
 
 static int pick_bn(int epi, int N) {
@@ -173,34 +209,42 @@ static int pick_bn(int epi, int N) {
 struct GemmPlan {
     int BN, CG;
     int MC = 1;     // 2: clusters of two CTA pairs that share (TMA-multicast) the weight tile
+    int sms = 0;    // SM count of the device the plan was made for (persistent grid size)
 };
 // DINO_B200_GEMM_MC=1 enables the weight-multicast variant for the large (256-wide, CTA-pair) tiles
 static int gemm_mc() {
+#ifdef DINO_B200_EXPERIMENTAL
     static int v = [] {
         const char *e = getenv("DINO_B200_GEMM_MC");
         return (e && e[0] == '1') ? 2 : 1;
     }();
     return v;
+#else
+    return 1;
+#endif
 }
-static GemmPlan plan_gemm(int epi, int M, int N) {
+static GemmPlan plan_gemm(int epi, int M, int N, int num_sms) {
     const int bn_big = pick_bn(epi, N);
     const GemmPlan cand[3] = {{bn_big, gemm_cg()}, {bn_big, 1}, {128, 1}};
     const int n_cand = (epi == EPI_SWIGLU_F16) ? 2 : 3;
     GemmPlan best = cand[0];
+    best.sms = num_sms;
     int best_busy = -1;
     for (int i = 0; i < n_cand; ++i) {
         const GemmPlan &c = cand[i];
         const int tiles = ((M + GEMM_BM * c.CG - 1) / (GEMM_BM * c.CG)) * ((N + c.BN - 1) / c.BN);
-        const int busy = std::min(tiles * c.CG, g_num_sms);
-        if (busy * 10 >= g_num_sms * 9) {           // enough work for (nearly) every SM: the widest such tile
+        const int busy = std::min(tiles * c.CG, num_sms);
+        if (busy * 10 >= num_sms * 9) {           // enough work for (nearly) every SM: the widest such tile
             GemmPlan r = c;
-            if (i == 0 && c.CG == 2 && c.BN == 256 && gemm_mc() == 2 && g_num_sms % 4 == 0 && epi != EPI_PATCH_F32 &&
-                epi != EPI_RESID_LN_F32 && tiles >= g_num_sms)
+            r.sms = num_sms;
+            if (i == 0 && c.CG == 2 && c.BN == 256 && gemm_mc() == 2 && num_sms % 4 == 0 && epi != EPI_PATCH_F32 &&
+                epi != EPI_RESID_LN_F32 && tiles >= num_sms)
                 r.MC = 2;
             return r;
         }
         if (busy > best_busy) {
             best = c;
+            best.sms = num_sms;
             best_busy = busy;
         }
     }
@@ -208,11 +252,11 @@ static GemmPlan plan_gemm(int epi, int M, int N) {
 }
 
 template <int BN, int EPI, int CG, int MC = 1>
-static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, cudaStream_t st) {
+static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, int num_sms, cudaStream_t st) {
     const int tiles = ((p.M + GEMM_BM * CG * MC - 1) / (GEMM_BM * CG * MC)) * ((p.N + BN - 1) / BN);   // per cluster
     // DINO_B200_GEMM_SMS=n restricts the persistent grid to n SMs (experiments: per-SM throughput vs L2 bandwidth share)
     static const int sm_cap = [] { const char *e = getenv("DINO_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();
-    const int sms = sm_cap > 0 ? std::min(sm_cap, g_num_sms) : g_num_sms;
+    const int sms = sm_cap > 0 ? std::min(sm_cap, num_sms) : num_sms;
     const int grid = std::max(1, std::min(tiles, sms / (CG * MC))) * CG * MC;      // persistent: one cluster per CG * MC SMs
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -246,25 +290,29 @@ static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CU
     if (!p.a_hint) p.a_hint = a_hint;
     if (!p.b_hint) p.b_hint = b_hint;
     const int BN = plan.BN;
+#ifdef DINO_B200_EXPERIMENTAL
     if (plan.MC == 2) {
-        if (epi == EPI_BIAS_F16) return launch_gemm_t<256, EPI_BIAS_F16, 2, 2>(tmA, tmB, tmC, p, st);
-        if (epi == EPI_GELU_F16) return launch_gemm_t<256, EPI_GELU_F16, 2, 2>(tmA, tmB, tmC, p, st);
-        if (epi == EPI_RESID_F32) return launch_gemm_t<256, EPI_RESID_F32, 2, 2>(tmA, tmB, tmC, p, st);
-        if (epi == EPI_SWIGLU_F16) return launch_gemm_t<256, EPI_SWIGLU_F16, 2, 2>(tmA, tmB, tmC, p, st);
+        if (epi == EPI_BIAS_F16) return launch_gemm_t<256, EPI_BIAS_F16, 2, 2>(tmA, tmB, tmC, p, plan.sms, st);
+        if (epi == EPI_GELU_F16) return launch_gemm_t<256, EPI_GELU_F16, 2, 2>(tmA, tmB, tmC, p, plan.sms, st);
+        if (epi == EPI_RESID_F32) return launch_gemm_t<256, EPI_RESID_F32, 2, 2>(tmA, tmB, tmC, p, plan.sms, st);
+        if (epi == EPI_SWIGLU_F16) return launch_gemm_t<256, EPI_SWIGLU_F16, 2, 2>(tmA, tmB, tmC, p, plan.sms, st);
         throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no multicast kernel for this epilogue");
     }
+#endif
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) throw StatusError(DINO_B200_ERR_INVALID, "gemm: empty problem");
     if (p.N % 8) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: N must be a multiple of 8");
 #define DINO_GEMM_CASE(bn, e) \
-    if (BN == bn && epi == e) return plan.CG == 2 ? launch_gemm_t<bn, e, 2>(tmA, tmB, tmC, p, st) : launch_gemm_t<bn, e, 1>(tmA, tmB, tmC, p, st)
+    if (BN == bn && epi == e) return plan.CG == 2 ? launch_gemm_t<bn, e, 2>(tmA, tmB, tmC, p, plan.sms, st) : launch_gemm_t<bn, e, 1>(tmA, tmB, tmC, p, plan.sms, st)
     DINO_GEMM_CASE(256, EPI_BIAS_F16);
     DINO_GEMM_CASE(128, EPI_BIAS_F16);
     DINO_GEMM_CASE(256, EPI_GELU_F16);
     DINO_GEMM_CASE(128, EPI_GELU_F16);
     DINO_GEMM_CASE(256, EPI_RESID_F32);
     DINO_GEMM_CASE(128, EPI_RESID_F32);
+#ifdef DINO_B200_EXPERIMENTAL
     DINO_GEMM_CASE(256, EPI_RESID_LN_F32);
     DINO_GEMM_CASE(128, EPI_RESID_LN_F32);
+#endif
     DINO_GEMM_CASE(256, EPI_SWIGLU_F16);
     DINO_GEMM_CASE(256, EPI_PATCH_F32);
     DINO_GEMM_CASE(128, EPI_PATCH_F32);
@@ -272,14 +320,18 @@ static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CU
     throw StatusError(DINO_B200_ERR_UNSUPPORTED, "gemm: no kernel for this (tile, epilogue) pair");
 }
 
-// DINO_B200_ATTN=3|5|7 selects another generation of the attention kernel for A/B comparisons (default: 8 = v5's TMEM ring
-// with intra-tile pipelining and packed-pair softmax arithmetic).  Per ViT-L layer at batch 64 on B200: v3 932 us, v4 885,
-// v5 780, v6 (16 softmax warps) 872, v7 (loads pipelined across tiles) 878, v8 724.  v1, v2, v4 and v6 were removed from the
-// tree after measurement (git history: attention.cuh, attention2.cuh, attention4.cuh, attention6.cuh).
+// The product library carries ONE attention kernel (v10: v8's tile loop run as one continuous stream across work items, one MMA
+// warp per query tile, deferred TMA-store epilogue, a third of the exponentials on the FMA pipe).  Per ViT-L layer at batch 64 on
+// B200: v3 932 us, v4 885, v5 780, v6 (16 softmax warps) 872, v7 878, v8 724, v9 (loop rotated by half a chunk) 817, v10 666-680.
+// v3 / v5 / v7 / v8 are only in -DDINO_B200_EXPERIMENTAL builds (DINO_B200_ATTN=3|5|7|8, tools/build_variant.sh); v1, v2, v4, v6
+// and v9 were removed from the tree after measurement (git history).
 static int attention_variant() {
     static int v = [] {
+#ifdef DINO_B200_EXPERIMENTAL
         const char *e = getenv("DINO_B200_ATTN");
-        return (e && (e[0] == '3' || e[0] == '5' || e[0] == '7')) ? e[0] - '0' : 8;
+        if (e && (e[0] == '3' || e[0] == '5' || e[0] == '7' || e[0] == '8')) return e[0] - '0';
+#endif
+        return 10;
     }();
     return v;
 }
@@ -298,72 +350,65 @@ static unsigned long long *attention_trace_buffer(cudaStream_t st) {
     return tr;
 }
 
-static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, cudaStream_t st) {
-    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
-    if (attention_variant() == 8) {
-        Attn8Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        ap.trace = nullptr;
+template <typename Params> static Params attention_params(__half *out, int B, int n_tok, int D) {
+    Params ap{};
+    ap.n_tok = n_tok;
+    ap.hidden = D;
+    ap.n_heads = D / ATT_HD;
+    ap.n_qblk = (n_tok + 255) / 256;
+    ap.num_items = B * ap.n_heads * ap.n_qblk;
+    ap.out = out;
+    ap.scale_log2 = (1.0f / sqrtf(static_cast<float>(ATT_HD))) * 1.4426950408889634f;
+    ap.trace = nullptr;
+    return ap;
+}
+
+static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, int num_sms, cudaStream_t st) {
+    const int variant = attention_variant();
+    if (variant == 10) {
+        Attn10Params ap = attention_params<Attn10Params>(out, B, n_tok, D);
+#if defined(AT10_TRACE) || defined(AT10_PROF)
+        ap.trace = attention_trace_buffer(st);
+#endif
+        const CUtensorMap tmOut = make_tmap_3d_f16(out, D, n_tok, B, D, ATT_BKV);
+        const int grid = std::max(1, std::min(ap.num_items, num_sms));
+        attention_fwd_v10<<<grid, AT10_THREADS, AT10_SMEM_BYTES, st>>>(tmQKV, tmOut, ap);
+    }
+#ifdef DINO_B200_EXPERIMENTAL
+    else if (variant == 8) {
+        Attn8Params ap = attention_params<Attn8Params>(out, B, n_tok, D);
 #ifdef AT8_TRACE
         ap.trace = attention_trace_buffer(st);
 #endif
-        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        const int grid = std::max(1, std::min(ap.num_items, num_sms));
         attention_fwd_v8<<<grid, AT8_THREADS, AT8_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 7) {
-        Attn7Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        ap.trace = nullptr;
+    } else if (variant == 7) {
+        Attn7Params ap = attention_params<Attn7Params>(out, B, n_tok, D);
 #ifdef AT7_TRACE
         ap.trace = attention_trace_buffer(st);
 #endif
-        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        const int grid = std::max(1, std::min(ap.num_items, num_sms));
         attention_fwd_v7<<<grid, AT7_THREADS, AT7_SMEM_BYTES, st>>>(tmQKV, ap);
-    } else if (attention_variant() == 5) {
-        Attn5Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
-        ap.trace = nullptr;
+    } else if (variant == 5) {
+        Attn5Params ap = attention_params<Attn5Params>(out, B, n_tok, D);
 #ifdef AT5_TRACE
         ap.trace = attention_trace_buffer(st);
 #endif
-        const int grid = std::max(1, std::min(ap.num_items, g_num_sms));
+        const int grid = std::max(1, std::min(ap.num_items, num_sms));
         attention_fwd_v5<<<grid, AT5_THREADS, AT5_SMEM_BYTES, st>>>(tmQKV, ap);
     } else {
-        Attn3Params ap;
-        ap.n_tok = n_tok;
-        ap.hidden = D;
-        ap.n_heads = D / ATT_HD;
-        ap.n_qblk = (n_tok + 255) / 256;
-        ap.num_items = B * ap.n_heads * ap.n_qblk;
-        ap.out = out;
-        ap.scale_log2 = scale_log2;
+        Attn3Params ap = attention_params<Attn3Params>(out, B, n_tok, D);
         static const int pingpong = [] { const char *e = getenv("DINO_B200_ATTN_PINGPONG"); return (e && e[0] == '1') ? 1 : 0; }();
         ap.pingpong = pingpong;
-        ap.trace = nullptr;
 #ifdef AT3_TRACE
         ap.trace = attention_trace_buffer(st);
 #endif
         static const int grid_mult = [] { const char *e = getenv("DINO_B200_ATTN_GRID"); return e ? atoi(e) : 1; }();
-        const int grid = grid_mult <= 0 ? ap.num_items : std::max(1, std::min(ap.num_items, g_num_sms * grid_mult));
+        const int grid = grid_mult <= 0 ? ap.num_items : std::max(1, std::min(ap.num_items, num_sms * grid_mult));
         attention_fwd_v3<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(tmQKV, ap);
     }
+#endif
+    (void) attention_trace_buffer;
     DINO_CUDA(cudaGetLastError());
 }
 
@@ -413,9 +458,30 @@ struct ProfileEvent {
 
 using namespace dino;
 
+// One captured forward pass: every pointer and shape a replay depends on is part of the key
+struct GraphKey {
+    const void *images;
+    int layout, B, H, W, flags;
+    const void *cls, *patch, *logits, *probs;
+    bool operator<(const GraphKey &o) const {
+        return std::tie(images, layout, B, H, W, flags, cls, patch, logits, probs) <
+               std::tie(o.images, o.layout, o.B, o.H, o.W, o.flags, o.cls, o.patch, o.logits, o.probs);
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;     // kernels per replay
+};
+
 struct dino_b200_engine {
     int device = 0;
+    int num_sms = 0;
     cudaStream_t stream = nullptr;
+    // CUDA-graph cache of whole forward passes (reference: dino_predict rebuilds and re-plans its ggml graph on every call,
+    // dinov2.cpp:907-942).  Dropped whenever a baked pointer may change (arena growth, new pos-embed table).
+    bool use_graphs = true;
+    std::map<GraphKey, GraphEntry> graphs;
+    uint64_t graph_replays = 0, graph_captures = 0;
     dino_b200_hparams hp{};
     bool swiglu = false;
     int mlp_in = 0, mlp_hidden = 0;
@@ -487,17 +553,35 @@ static void h2d(dino_b200_engine *e, void *dst, const void *src, size_t bytes) {
     DINO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
 }
 
+// Every dimension of a checkpoint tensor must be positive and the element count must fit comfortably in 63 bits;
+// callers divide by ne[0] and size buffers from these numbers.
 static int64_t numel(const dino_b200_tensor &t) {
+    if (t.n_dims < 1 || t.n_dims > 4) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + (t.name ? t.name : "?") + "' has a bad rank");
     int64_t n = 1;
-    for (int d = 0; d < t.n_dims; ++d) n *= t.ne[d];
+    for (int d = 0; d < t.n_dims; ++d) {
+        if (t.ne[d] <= 0 || t.ne[d] > (int64_t(1) << 40) || n > (int64_t(1) << 62) / t.ne[d])
+            throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + (t.name ? t.name : "?") + "' has a bad dimension");
+        n *= t.ne[d];
+    }
     return n;
 }
+
+// Scratch device allocation that is released on every exit path (conversion temporaries of the loader)
+struct DeviceTemp {
+    void *p = nullptr;
+    explicit DeviceTemp(size_t bytes) { DINO_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
+    ~DeviceTemp() { if (p) cudaFree(p); }
+    DeviceTemp(const DeviceTemp &) = delete;
+    DeviceTemp &operator=(const DeviceTemp &) = delete;
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
 
 static float *upload_f32(dino_b200_engine *e, const dino_b200_tensor &t, int64_t expect, const std::vector<int> *perm = nullptr) {
     if (t.type != DINO_B200_TYPE_F32) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + t.name + "' must be F32");
     if (numel(t) != expect)
         throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + t.name + "' has " + std::to_string(numel(t)) +
                                                     " elements, expected " + std::to_string(expect));
+    if (!t.data) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + t.name + "' has no data");
     float *d = static_cast<float *>(e->dmalloc(expect * sizeof(float)));
     if (perm) {
         std::vector<float> tmp(expect);
@@ -513,53 +597,58 @@ static float *upload_f32(dino_b200_engine *e, const dino_b200_tensor &t, int64_t
 // Weight matrix [N, K] (ggml ne = [K, N], or [14,14,3,N] for the patch projection) -> device fp16 [N, ldw].
 static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor &w, const dino_b200_tensor &b, int N, int K,
                           int epi, const std::vector<int> *perm, bool want_tmap = true) {
+    const int64_t n_w = numel(w);                    // validates the dimensions (all positive)
     int64_t k_file = w.ne[0];
     if (w.n_dims == 4) k_file = w.ne[0] * w.ne[1] * w.ne[2];
-    const int64_t n_file = numel(w) / k_file;
+    const int64_t n_file = n_w / k_file;
     if (k_file != K || n_file != N)
         throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' is [" + std::to_string(n_file) + ", " +
                                                     std::to_string(k_file) + "], expected [" + std::to_string(N) + ", " +
                                                     std::to_string(K) + "]");
+    if (!w.data) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' has no data");
     L.N = N;
     L.K = K;
     L.ldw = (K + 63) / 64 * 64;
     L.BN = pick_bn(epi, N);
     L.w = static_cast<__half *>(e->dmalloc(static_cast<size_t>(N) * L.ldw * sizeof(__half)));
+    std::unique_ptr<DeviceTemp> d_perm_buf;
     int *d_perm = nullptr;
     if (perm) {
-        DINO_CUDA(cudaMalloc(&d_perm, N * sizeof(int)));
+        d_perm_buf.reset(new DeviceTemp(N * sizeof(int)));
+        d_perm = d_perm_buf->as<int>();
         h2d(e, d_perm, perm->data(), N * sizeof(int));
     }
-    const int grid = g_num_sms * 8;
+    const int grid = e->num_sms * 8;
     if (w.type == DINO_B200_TYPE_F16) {
+        if (w.nbytes && w.nbytes < static_cast<uint64_t>(N) * K * sizeof(__half)) throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' is shorter than its shape");
         if (!perm && L.ldw == K) {
             h2d(e, L.w, w.data, static_cast<size_t>(N) * K * sizeof(__half));
         } else {
-            __half *tmp = nullptr;
-            DINO_CUDA(cudaMalloc(&tmp, static_cast<size_t>(N) * K * sizeof(__half)));
-            h2d(e, tmp, w.data, static_cast<size_t>(N) * K * sizeof(__half));
-            copy_rows_f16_kernel<<<grid, 256, 0, e->stream>>>(tmp, L.w, N, K, L.ldw, d_perm);
+            DeviceTemp tmp(static_cast<size_t>(N) * K * sizeof(__half));
+            h2d(e, tmp.p, w.data, static_cast<size_t>(N) * K * sizeof(__half));
+            copy_rows_f16_kernel<<<grid, 256, 0, e->stream>>>(tmp.as<__half>(), L.w, N, K, L.ldw, d_perm);
             DINO_CUDA(cudaGetLastError());
             DINO_CUDA(cudaStreamSynchronize(e->stream));
-            DINO_CUDA(cudaFree(tmp));
         }
     } else if (w.type == DINO_B200_TYPE_Q8_0 || w.type == DINO_B200_TYPE_Q4_0 || w.type == DINO_B200_TYPE_Q4_1 ||
                w.type == DINO_B200_TYPE_Q5_0 || w.type == DINO_B200_TYPE_Q5_1) {
         if (K % 32 || L.ldw != K) throw StatusError(DINO_B200_ERR_FORMAT, std::string("quantised tensor '") + w.name + "' has an unsupported row length");
-        uint8_t *raw = nullptr;
-        DINO_CUDA(cudaMalloc(&raw, w.nbytes));
-        h2d(e, raw, w.data, w.nbytes);
+        static const int kBlockBytes[9] = {0, 0, 18, 20, 0, 0, 22, 24, 34};
         const long long nblk = static_cast<long long>(N) * (K / 32);
+        const uint64_t need = static_cast<uint64_t>(nblk) * kBlockBytes[w.type];
+        if (w.nbytes < need) throw StatusError(DINO_B200_ERR_FORMAT, std::string("quantised tensor '") + w.name + "' is shorter than its shape");
+        DeviceTemp raw(need);
+        h2d(e, raw.p, w.data, need);
+        const uint8_t *rp = raw.as<uint8_t>();
         switch (w.type) {
-            case DINO_B200_TYPE_Q4_0: dequant_kernel<2><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
-            case DINO_B200_TYPE_Q4_1: dequant_kernel<3><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
-            case DINO_B200_TYPE_Q5_0: dequant_kernel<6><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
-            case DINO_B200_TYPE_Q5_1: dequant_kernel<7><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
-            default: dequant_kernel<8><<<grid, 256, 0, e->stream>>>(raw, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q4_0: dequant_kernel<2><<<grid, 256, 0, e->stream>>>(rp, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q4_1: dequant_kernel<3><<<grid, 256, 0, e->stream>>>(rp, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q5_0: dequant_kernel<6><<<grid, 256, 0, e->stream>>>(rp, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            case DINO_B200_TYPE_Q5_1: dequant_kernel<7><<<grid, 256, 0, e->stream>>>(rp, L.w, nblk, K / 32, L.ldw, d_perm); break;
+            default: dequant_kernel<8><<<grid, 256, 0, e->stream>>>(rp, L.w, nblk, K / 32, L.ldw, d_perm); break;
         }
         DINO_CUDA(cudaGetLastError());
         DINO_CUDA(cudaStreamSynchronize(e->stream));
-        DINO_CUDA(cudaFree(raw));
     } else if (w.type == DINO_B200_TYPE_F32) {
         std::vector<__half> h(static_cast<size_t>(N) * L.ldw, __float2half(0.f));
         const float *src = static_cast<const float *>(w.data);
@@ -572,8 +661,8 @@ static void upload_linear(dino_b200_engine *e, Linear &L, const dino_b200_tensor
     } else {
         throw StatusError(DINO_B200_ERR_FORMAT, std::string("tensor '") + w.name + "' has unsupported type " + std::to_string(w.type));
     }
-    DINO_CUDA(cudaStreamSynchronize(e->stream));
-    if (d_perm) DINO_CUDA(cudaFree(d_perm));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));     // the temporaries above are released only after their last use
+    d_perm_buf.reset();
     L.bias = upload_f32(e, b, N, perm);
     // logical K columns = ldw: the pad columns are real zeros, so the K loop needs no tail case
     if (want_tmap) {
@@ -622,6 +711,7 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
                       EPI_RESID_F32, nullptr);
         if (e->swiglu) {
             const dino_b200_tensor &win = tt.at(b + "mlp.weights_in.weight");
+            if (win.n_dims < 2 || win.ne[1] <= 0 || win.ne[1] > (1 << 20)) throw StatusError(DINO_B200_ERR_FORMAT, "mlp.weights_in.weight has a bad shape");
             const int n_in = static_cast<int>(win.ne[1]);
             if (n_in % 256) throw StatusError(DINO_B200_ERR_UNSUPPORTED, "SwiGLU hidden size must be a multiple of 128");
             const int hid = n_in / 2;
@@ -637,6 +727,7 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
             upload_linear(e, ly.fc2, tt.at(b + "mlp.weights_out.weight"), tt.at(b + "mlp.weights_out.bias"), D, hid, EPI_RESID_F32, nullptr);
         } else {
             const dino_b200_tensor &w1 = tt.at(b + "mlp.fc1.weight");
+            if (w1.n_dims < 2 || w1.ne[1] <= 0 || w1.ne[1] > (1 << 20)) throw StatusError(DINO_B200_ERR_FORMAT, "mlp.fc1.weight has a bad shape");
             const int n_in = static_cast<int>(w1.ne[1]);
             e->mlp_in = n_in;
             e->mlp_hidden = n_in;
@@ -656,7 +747,9 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
 }
 
 // ------------------------------------------------------------------------------------------------ arena
+static void drop_graphs(dino_b200_engine *e);
 static void free_arena(dino_b200_engine *e) {
+    drop_graphs(e);                                         // captured forwards hold arena pointers
     void *ptrs[] = {e->d_img, e->X, e->Y, e->feat, e->logits, e->probs, e->Ape, e->Xn, e->QKV, e->AO, e->H1, e->o_cls, e->o_patch, e->ln_count};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -740,34 +833,24 @@ struct Prof {
     }
 };
 
-static void forward_device(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
-                           float *patch, float *logits, float *probs, cudaStream_t st) {
+static void drop_graphs(dino_b200_engine *e) {
+    for (auto &kv : e->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+}
+
+// Enqueues one forward pass on `st` (kernel launches and device-to-device copies only: capturable).  Returns the number of
+// kernels launched.  `pos` is the position-embedding table for this grid (pos_for_grid, resolved by the caller).
+static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
+                                float *patch, float *logits, float *probs, const float *pos, cudaStream_t st) {
     const dino_b200_hparams &hp = e->hp;
     const int ps = hp.patch_size, D = hp.hidden_size, R = hp.num_register_tokens;
-    if (!images || B <= 0 || H < ps || W < ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: bad batch or image size");
-    if (H % ps || W % ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: image size must be a multiple of the patch size");
-    if (layout != DINO_B200_LAYOUT_RGB_PLANAR && layout != DINO_B200_LAYOUT_BGR_HWC) throw StatusError(DINO_B200_ERR_INVALID, "forward: unknown image layout");
     const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
-    if ((logits || probs) && !classify) throw StatusError(DINO_B200_ERR_INVALID, "forward: logits/probs require DINO_B200_CLASSIFY");
-    if (classify && !e->wc) throw StatusError(DINO_B200_ERR_INVALID, "forward: checkpoint has no classifier head");
-
+    const int g_num_sms = e->num_sms;
     const int gh = H / ps, gw = W / ps, np = gh * gw, ntok = 1 + R + np;
     const int M = B * ntok, Mp = B * np;
-    // every kernel launched below belongs to this engine; count them as we go
-    uint64_t &nl = e->launches;
+    uint64_t nl = 0;
     Prof prof{e, st};
-    if (e->profiling) {
-        for (auto &pe : e->prof) e->prof_pool.push_back(pe);
-        e->prof.clear();
-        if (!e->ev_t0) {
-            DINO_CUDA(cudaEventCreate(&e->ev_t0));
-            DINO_CUDA(cudaEventCreate(&e->ev_t1));
-        }
-        DINO_CUDA(cudaEventRecord(e->ev_t0, st));
-    }
-
-    const float *pos = pos_for_grid(e, gh, gw);
-    if (st != e->stream) DINO_CUDA(cudaStreamSynchronize(e->stream));   // pos-embed resample ran on the engine stream
 
     const CUtensorMap tm_ape = make_tmap_f16(e->Ape, e->patch.ldw, Mp, e->patch.ldw, GEMM_BM);
     const CUtensorMap tm_xn = make_tmap_f16(e->Xn, D, M, D, GEMM_BM);
@@ -794,7 +877,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         gp.bias = e->patch.bias; gp.out = e->X; gp.ldo = D;
         gp.pos = pos; gp.np = np; gp.ntok = ntok; gp.tok_off = 1 + R;
         prof.begin(0);
-        const GemmPlan pl = plan_gemm(EPI_PATCH_F32, gp.M, gp.N);
+        const GemmPlan pl = plan_gemm(EPI_PATCH_F32, gp.M, gp.N, g_num_sms);
         launch_gemm(EPI_PATCH_F32, pl, tm_ape, e->patch.tm(pl), tmo_x, gp, st);
         prof.end();
         nl++;
@@ -811,7 +894,11 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
     // measured on B200 it is slower (o-proj + LN 857 us fused vs 186 + 99 us apart at ViT-L, batch 64): the 8 epilogue
     // warps of a CTA normalise a 128-row block at ~17 GB/s (latency-bound L2 read-back), and because the CTA that
     // finishes a row block LAST does the work, it keeps landing on the CTAs that are already behind.
+#ifdef DINO_B200_EXPERIMENTAL
     static const bool fuse_ln = [] { const char *e = getenv("DINO_B200_FUSE_LN"); return e && e[0] == '1'; }();
+#else
+    constexpr bool fuse_ln = false;
+#endif
     const size_t n_layers = e->layers.size();
     for (size_t li = 0; li < n_layers; ++li) {
         const Layer &ly = e->layers[li];
@@ -825,12 +912,12 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             GemmParams gp{};
             gp.M = M; gp.N = 3 * D; gp.K = D; gp.bias = ly.qkv.bias; gp.out = e->QKV; gp.ldo = 3 * D;
             prof.begin(0);
-            const GemmPlan pl = plan_gemm(EPI_BIAS_F16, gp.M, gp.N);
+            const GemmPlan pl = plan_gemm(EPI_BIAS_F16, gp.M, gp.N, g_num_sms);
             launch_gemm(EPI_BIAS_F16, pl, tm_xn, ly.qkv.tm(pl), tmo_qkv, gp, st);
             prof.end();
         }
         prof.begin(1);
-        launch_attention(tm_qkv, e->AO, B, ntok, D, st);
+        launch_attention(tm_qkv, e->AO, B, ntok, D, g_num_sms, st);
         prof.end();
         {
             GemmParams gp{};
@@ -838,7 +925,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             gp.ln_gamma = ly.ln2_g; gp.ln_beta = ly.ln2_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
             prof.begin(0);
             const int epi = fuse_ln ? EPI_RESID_LN_F32 : EPI_RESID_F32;
-            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N, g_num_sms);
             launch_gemm(epi, pl, tm_ao, ly.proj.tm(pl), tmo_x, gp, st);
             prof.end();
         }
@@ -853,7 +940,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             gp.M = M; gp.N = e->mlp_in; gp.K = D; gp.bias = ly.fc1.bias; gp.out = e->H1; gp.ldo = e->mlp_hidden;
             prof.begin(0);
             const int epi = e->swiglu ? EPI_SWIGLU_F16 : EPI_GELU_F16;
-            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N, g_num_sms);
             launch_gemm(epi, pl, tm_xn, ly.fc1.tm(pl), tmo_h1, gp, st);
             prof.end();
         }
@@ -867,7 +954,7 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
             }
             prof.begin(0);
             const int epi = fuse_next ? EPI_RESID_LN_F32 : EPI_RESID_F32;
-            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N);
+            const GemmPlan pl = plan_gemm(epi, gp.M, gp.N, g_num_sms);
             launch_gemm(epi, pl, tm_h1, ly.fc2.tm(pl), tmo_x, gp, st);
             prof.end();
         }
@@ -900,7 +987,72 @@ static void forward_device(dino_b200_engine *e, const float *images, int layout,
         }
     }
     prof.end();
-    if (e->profiling) DINO_CUDA(cudaEventRecord(e->ev_t1, st));
+    return nl;
+}
+
+// DINO_B200_GRAPH=0 disables CUDA-graph replay (every forward then enqueues its ~7 L + 6 kernels one by one)
+static bool graphs_enabled() {
+    static const bool v = [] { const char *e = getenv("DINO_B200_GRAPH"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+static void forward_device(dino_b200_engine *e, const float *images, int layout, int B, int H, int W, int flags, float *cls,
+                           float *patch, float *logits, float *probs, cudaStream_t st) {
+    const dino_b200_hparams &hp = e->hp;
+    const int ps = hp.patch_size;
+    if (!images || B <= 0 || H < ps || W < ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: bad batch or image size");
+    if (H % ps || W % ps) throw StatusError(DINO_B200_ERR_INVALID, "forward: image size must be a multiple of the patch size");
+    if (layout != DINO_B200_LAYOUT_RGB_PLANAR && layout != DINO_B200_LAYOUT_BGR_HWC) throw StatusError(DINO_B200_ERR_INVALID, "forward: unknown image layout");
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    if ((logits || probs) && !classify) throw StatusError(DINO_B200_ERR_INVALID, "forward: logits/probs require DINO_B200_CLASSIFY");
+    if (classify && !e->wc) throw StatusError(DINO_B200_ERR_INVALID, "forward: checkpoint has no classifier head");
+
+    const size_t n_pos_tables = e->pos_cache.size();
+    const float *pos = pos_for_grid(e, H / ps, W / ps);        // may launch the bicubic resample on the engine stream (first use of a grid)
+    if (e->pos_cache.size() != n_pos_tables && st != e->stream) DINO_CUDA(cudaStreamSynchronize(e->stream));
+
+    if (e->profiling) {
+        // per-kernel event pairs (bench roofline / tools): direct launches, never a graph
+        for (auto &pe : e->prof) e->prof_pool.push_back(pe);
+        e->prof.clear();
+        if (!e->ev_t0) {
+            DINO_CUDA(cudaEventCreate(&e->ev_t0));
+            DINO_CUDA(cudaEventCreate(&e->ev_t1));
+        }
+        DINO_CUDA(cudaEventRecord(e->ev_t0, st));
+        e->launches += forward_enqueue(e, images, layout, B, H, W, flags, cls, patch, logits, probs, pos, st);
+        DINO_CUDA(cudaEventRecord(e->ev_t1, st));
+        return;
+    }
+    if (!e->use_graphs || !graphs_enabled()) {
+        e->launches += forward_enqueue(e, images, layout, B, H, W, flags, cls, patch, logits, probs, pos, st);
+        return;
+    }
+    const GraphKey key{images, layout, B, H, W, flags, cls, patch, logits, probs};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        if (e->graphs.size() >= 16) drop_graphs(e);            // callers that cycle through many buffers: start over
+        GraphEntry ge;
+        cudaGraph_t graph = nullptr;
+        DINO_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            ge.launches = forward_enqueue(e, images, layout, B, H, W, flags, cls, patch, logits, probs, pos, st);
+        } catch (...) {
+            cudaStreamEndCapture(st, &graph);                  // leave capture mode before reporting
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            throw;
+        }
+        DINO_CUDA(cudaStreamEndCapture(st, &graph));
+        const cudaError_t ierr = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ierr != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ierr));
+        e->graph_captures++;
+        it = e->graphs.emplace(key, ge).first;
+    }
+    DINO_CUDA(cudaGraphLaunch(it->second.exec, st));
+    e->graph_replays++;
+    e->launches += it->second.launches;
 }
 
 }  // namespace dino
@@ -973,9 +1125,10 @@ dino_b200_status dino_b200_create(const dino_b200_model_desc *desc, int device, 
     dino_b200_engine *e = nullptr;
     DINO_API_BEGIN
     DINO_CUDA(cudaSetDevice(device));
-    configure_kernels_once();
+    const int num_sms = configure_current_device();
     e = new dino_b200_engine();
     e->device = device;
+    e->num_sms = num_sms;
     DINO_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     try {
         build_engine(e, desc);
@@ -1034,15 +1187,25 @@ dino_b200_status dino_b200_create_from_gguf(const char *path, int device, dino_b
     }
     desc.n_tensors = static_cast<int32_t>(ts.size());
     desc.tensors = ts.data();
-    const dino_b200_status st = dino_b200_create(&desc, device, out);
-    if (st == DINO_B200_OK) {
-        (*out)->labels.resize(hp.num_classes);
-        for (uint32_t i = 0; i < hp.num_classes; ++i) {
-            auto it = gg.kv_s.find(std::to_string(i));
-            if (it != gg.kv_s.end()) (*out)->labels[i] = it->second;
+    // a class count without a matching classifier head is a malformed checkpoint, not an allocation request
+    if (hp.num_classes > 0) {
+        const dino::GGUFTensorInfo *cw = gg.find("classifier.weight");
+        if (!cw || cw->n_dims < 2 || static_cast<uint64_t>(cw->ne[1]) != hp.num_classes) {
+            dino::g_last_error = "gguf: num_classes does not match the classifier.weight tensor";
+            return DINO_B200_ERR_FORMAT;
         }
     }
-    return st;
+    const dino_b200_status st = dino_b200_create(&desc, device, out);
+    if (st != DINO_B200_OK) return st;
+    dino_b200_engine *eng = *out;
+    DINO_API_BEGIN
+    eng->labels.resize(hp.num_classes);
+    for (uint32_t i = 0; i < hp.num_classes; ++i) {
+        auto it = gg.kv_s.find(std::to_string(i));
+        if (it != gg.kv_s.end()) eng->labels[i] = it->second;
+    }
+    return DINO_B200_OK;
+    DINO_API_END(eng)
 }
 
 dino_b200_status dino_b200_quantize_gguf(const char *fname_inp, const char *fname_out, int ggml_type) {
@@ -1394,8 +1557,8 @@ dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int lda, const vo
     int dev = 0;
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
-    configure_kernels_once();
-    const dino::GemmPlan pl = dino::plan_gemm(epi, M, N);
+    const int num_sms = configure_current_device();
+    const dino::GemmPlan pl = dino::plan_gemm(epi, M, N, num_sms);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
     const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG / pl.MC);
     dino::GemmParams gp{};
@@ -1413,14 +1576,21 @@ dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const vo
                                                 const float *lscale, float *X, const float *gamma, const float *beta, float eps,
                                                 void *ln_out, int *counters, void *stream) {
     DINO_API_BEGIN
+#ifndef DINO_B200_EXPERIMENTAL
+    (void) A; (void) lda; (void) W; (void) ldw; (void) M; (void) N; (void) K; (void) bias; (void) lscale; (void) X; (void) gamma;
+    (void) beta; (void) eps; (void) ln_out; (void) counters; (void) stream;
+    throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED,
+                            "kernel_gemm_resid_ln: the fused residual + LayerNorm epilogue measured slower than the two kernels apart "
+                            "and is only compiled with -DDINO_B200_EXPERIMENTAL");
+#else
     if (!A || !W || !X || !bias || !lscale || !gamma || !beta || !ln_out || !counters)
         throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_gemm_resid_ln: NULL argument");
     if (N % 128 || N > 128 * dino::LN_MAX_V4) throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED, "kernel_gemm_resid_ln: N must be a multiple of 128, at most 1536");
     int dev = 0;
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
-    configure_kernels_once();
-    const dino::GemmPlan pl = dino::plan_gemm(dino::EPI_RESID_LN_F32, M, N);
+    const int num_sms = configure_current_device();
+    const dino::GemmPlan pl = dino::plan_gemm(dino::EPI_RESID_LN_F32, M, N, num_sms);
     const CUtensorMap tmA = dino::make_tmap_f16(A, K, M, lda, GEMM_BM);
     const CUtensorMap tmB = dino::make_tmap_f16(W, K, N, ldw, pl.BN / pl.CG);
     dino::GemmParams gp{};
@@ -1429,6 +1599,7 @@ dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const vo
     const CUtensorMap tmC = dino::make_tmap_out(dino::EPI_RESID_LN_F32, X, N, M, N);
     dino::launch_gemm(dino::EPI_RESID_LN_F32, pl, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
+#endif
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }
 
@@ -1438,9 +1609,9 @@ dino_b200_status dino_b200_kernel_attention(const void *qkv, void *out, int B, i
     int dev = 0;
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
-    configure_kernels_once();
+    const int num_sms = configure_current_device();
     const CUtensorMap tm = dino::make_tmap_2d(qkv, false, 3 * D, static_cast<uint64_t>(B) * n_tok, 3 * D, ATT_BKV, dino::attn_promotion());
-    dino::launch_attention(tm, static_cast<__half *>(out), B, n_tok, D, static_cast<cudaStream_t>(stream));
+    dino::launch_attention(tm, static_cast<__half *>(out), B, n_tok, D, num_sms, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }
@@ -1477,7 +1648,7 @@ static void preprocess_device(dino_b200_engine *e, int B, int H, int W, bool cla
     const float3 mean = make_float3(0.406f, 0.456f, 0.485f);
     const float3 inv_std = make_float3(1.0f / 0.225f, 1.0f / 0.224f, 1.0f / 0.229f);
     const long long total = static_cast<long long>(B) * OH * OW;
-    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(g_num_sms) * 32));
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(e->num_sms) * 32));
     preprocess_bicubic_kernel<<<grid, 256, 0, e->stream>>>(e->d_u8, e->d_img, B, H, W, RH, RW, OH, OW, cy, cx, mean, inv_std);
     DINO_CUDA(cudaGetLastError());
     e->launches++;

@@ -46,7 +46,7 @@ struct Cursor {
     const uint8_t *p;
     const uint8_t *end;
     template <typename T> T take() {
-        if (p + sizeof(T) > end) throw std::runtime_error("gguf: truncated file");
+        if (static_cast<size_t>(end - p) < sizeof(T)) throw std::runtime_error("gguf: truncated file");
         T v;
         std::memcpy(&v, p, sizeof(T));
         p += sizeof(T);
@@ -82,6 +82,10 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
     if (!f) throw std::runtime_error("cannot open '" + path + "'");
     std::fseek(f, 0, SEEK_END);
     const long sz = std::ftell(f);
+    if (sz < 0) {
+        std::fclose(f);
+        throw std::runtime_error("cannot open '" + path + "': not a regular file");
+    }
     std::fseek(f, 0, SEEK_SET);
     out.blob.resize(static_cast<size_t>(sz));
     const size_t got = std::fread(out.blob.data(), 1, out.blob.size(), f);
@@ -95,6 +99,10 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
     out.version = version;
     const uint64_t n_tensors = c.take<uint64_t>();
     const uint64_t n_kv = c.take<uint64_t>();
+    // every KV record takes >= 12 bytes (key length, type, one value byte) and every tensor record >= 32: counts that cannot
+    // fit in the file are rejected before anything is sized by them
+    const uint64_t remaining = static_cast<uint64_t>(c.end - c.p);
+    if (n_kv > remaining / 12 || n_tensors > remaining / 32) throw std::runtime_error("gguf: tensor / KV count exceeds the file size");
 
     auto skip_or_read = [&](auto &&self, const std::string &key, uint32_t t, bool store) -> void {
         switch (t) {
@@ -110,6 +118,8 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
             case 9: {
                 const uint32_t et = c.take<uint32_t>();
                 const uint64_t n = c.take<uint64_t>();
+                if (et == 9) throw std::runtime_error("gguf: nested arrays are not supported");
+                if (n > static_cast<uint64_t>(c.end - c.p)) throw std::runtime_error("gguf: array length exceeds the file size");
                 for (uint64_t i = 0; i < n; ++i) self(self, key, et, false);
                 break;
             }
@@ -131,21 +141,38 @@ inline void gguf_read(const std::string &path, GGUFFile &out) {
         t.name = c.str();
         t.n_dims = static_cast<int32_t>(c.take<uint32_t>());
         if (t.n_dims < 1 || t.n_dims > 4) throw std::runtime_error("gguf: bad n_dims for " + t.name);
-        for (int d = 0; d < t.n_dims; ++d) t.ne[d] = static_cast<int64_t>(c.take<uint64_t>());
+        // dimensions: positive, and small enough that no product below can wrap (the whole file is < 2^63 bytes)
+        constexpr uint64_t kMaxDim = 1ull << 40;
+        for (int d = 0; d < t.n_dims; ++d) {
+            const uint64_t v = c.take<uint64_t>();
+            if (v == 0 || v > kMaxDim) throw std::runtime_error("gguf: bad dimension for " + t.name);
+            t.ne[d] = static_cast<int64_t>(v);
+        }
         t.type = static_cast<int32_t>(c.take<uint32_t>());
         t.offset = c.take<uint64_t>();
         uint64_t rows = 1;
-        for (int d = 1; d < t.n_dims; ++d) rows *= static_cast<uint64_t>(t.ne[d]);
-        t.nbytes = type_row_bytes(t.type, t.ne[0]) * rows;
+        for (int d = 1; d < t.n_dims; ++d) {
+            if (rows > out.blob.size() / static_cast<uint64_t>(t.ne[d]) + 1) throw std::runtime_error("gguf: tensor larger than the file: " + t.name);
+            rows *= static_cast<uint64_t>(t.ne[d]);
+        }
+        const uint64_t row_bytes = type_row_bytes(t.type, t.ne[0]);
+        if (row_bytes == 0 || rows > out.blob.size() / row_bytes) throw std::runtime_error("gguf: tensor larger than the file: " + t.name);
+        t.nbytes = row_bytes * rows;
     }
     uint64_t align = 32;
     auto it = out.kv_u.find("general.alignment");
     if (it != out.kv_u.end() && it->second) align = it->second;
+    if (align > (1u << 20) || (align & (align - 1))) throw std::runtime_error("gguf: general.alignment is not a power of two <= 1 MiB");
     out.alignment = align;
+    const uint64_t size = out.blob.size();
     const uint64_t meta = static_cast<uint64_t>(c.p - out.blob.data());
     const uint64_t data_start = (meta + align - 1) / align * align;
+    if (data_start > size && !out.tensors.empty()) throw std::runtime_error("gguf: truncated file (no data section)");
     for (auto &t : out.tensors) {
-        if (data_start + t.offset + t.nbytes > out.blob.size()) throw std::runtime_error("gguf: tensor data out of range: " + t.name);
+        // overflow-safe: offset <= size - data_start, nbytes <= size - data_start - offset
+        if (t.offset > size - data_start || t.nbytes > size - data_start - t.offset)
+            throw std::runtime_error("gguf: tensor data out of range: " + t.name);
+        if (t.offset % align) throw std::runtime_error("gguf: tensor data is not aligned: " + t.name);
         t.data = out.blob.data() + data_start + t.offset;
     }
 }

@@ -394,6 +394,12 @@ __device__ __forceinline__ f32x2 add2_f32(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
     return d;
 }
+// volatile flavour: keeps its program order relative to ex2_approx_ordered (software-pipeline distance of the softmax loop)
+__device__ __forceinline__ f32x2 add2_f32_ordered(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
 
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {

@@ -77,3 +77,66 @@ def test_malformed_checkpoints_are_reported_before_any_device_work(tmp_path):
             d.Engine(str(path))
         assert ei.value.status == want, (name, ei.value.status, str(ei.value))
         assert str(ei.value)                                          # a message, not just a code
+
+
+def _tensor_info_fields(blob: bytes):
+    """Byte offsets of every tensor-info field in a GGUF file: [(name, [ne offsets], type offset, data-offset offset)] and
+    the offset of the header's tensor count; plus {key: value offset} of the scalar KVs."""
+    import struct
+    pos = 8
+    n_tensors, n_kv = struct.unpack_from("<QQ", blob, pos)
+    pos += 16
+    sizes = {0: 1, 1: 1, 2: 2, 3: 2, 4: 4, 5: 4, 6: 4, 7: 1, 10: 8, 11: 8, 12: 8}
+    kv_off = {}
+    for _ in range(n_kv):
+        n = struct.unpack_from("<Q", blob, pos)[0]
+        key = blob[pos + 8: pos + 8 + n].decode()
+        pos += 8 + n
+        t = struct.unpack_from("<I", blob, pos)[0]
+        pos += 4
+        kv_off[key] = pos
+        if t == 8:
+            pos += 8 + struct.unpack_from("<Q", blob, pos)[0]
+        else:
+            pos += sizes[t]
+    infos = []
+    for _ in range(n_tensors):
+        n = struct.unpack_from("<Q", blob, pos)[0]
+        name = blob[pos + 8: pos + 8 + n].decode()
+        pos += 8 + n
+        nd = struct.unpack_from("<I", blob, pos)[0]
+        pos += 4
+        ne = [pos + 8 * i for i in range(nd)]
+        pos += 8 * nd
+        infos.append((name, ne, pos, pos + 4))
+        pos += 12
+    return infos, kv_off
+
+
+def test_hostile_tensor_tables_are_rejected(tmp_path):
+    """Overflow-safe range checks of the GGUF reader (round-1 advisor finding): a data offset that wraps in uint64, zero
+    or absurd dimensions, counts larger than the file, a misaligned offset and a class count without a classifier head are
+    all format errors — never an out-of-bounds upload, a division by zero or an exception across the C ABI."""
+    import struct
+    good = bytearray(open(os.path.join(ROOT, "tests", "golden", "tiny_f16.gguf"), "rb").read())
+    infos, kv_off = _tensor_info_fields(bytes(good))
+    by_name = {i[0]: i for i in infos}
+    qkv = by_name["encoder.layer.0.attention.attention.qkv.weight"]
+    cases = {}
+
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[3], 2**64 - 4096); cases["wrapping_offset"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[3], len(good)); cases["offset_past_end"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[3], struct.unpack_from("<Q", good, qkv[3])[0] + 2); cases["misaligned_offset"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[1][0], 0); cases["zero_dimension"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[1][1], 2**63); cases["huge_dimension"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, qkv[1][1], 2**33); cases["rows_overflow"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, 8, 2**60); cases["tensor_count_overflow"] = b
+    b = bytearray(good); struct.pack_into("<Q", b, 16, 2**60); cases["kv_count_overflow"] = b
+    b = bytearray(good); struct.pack_into("<I", b, kv_off["num_classes"], 0xFFFFFFFF); cases["class_count_without_head"] = b
+    for name, blob in cases.items():
+        path = tmp_path / (name + ".gguf")
+        path.write_bytes(bytes(blob))
+        with pytest.raises(d.DinoB200Error) as ei:
+            d.Engine(str(path))
+        assert ei.value.status == 3, (name, ei.value.status, str(ei.value))       # DINO_B200_ERR_FORMAT
+        assert str(ei.value), name

@@ -218,8 +218,13 @@ def test_gemm_residual_with_fused_layernorm(M, N, K):
     for rep in range(2):                                    # second launch: the counters must have been left at zero
         X = X0.clone()
         ln = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
-        E.kernel_gemm_resid_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), X.data_ptr(),
-                               gam.data_ptr(), bet.data_ptr(), 1e-6, ln.data_ptr(), cnt.data_ptr())
+        try:
+            E.kernel_gemm_resid_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), X.data_ptr(),
+                                   gam.data_ptr(), bet.data_ptr(), 1e-6, ln.data_ptr(), cnt.data_ptr())
+        except E.DinoB200Error as ex:
+            if ex.status == 5:      # DINO_B200_ERR_UNSUPPORTED: product builds leave this measured-slower experiment out
+                pytest.skip("fused residual + LayerNorm epilogue is only in -DDINO_B200_EXPERIMENTAL builds")
+            raise
         torch.cuda.synchronize()
         want = X0 + ls * ref
         assert nmse_t(X, want) < 1e-11
