@@ -7,5 +7,5 @@ Layout:
   gguf_io.py GGUF reader/writer, synth.py deterministic synthetic checkpoints / inputs
 """
 from . import gguf_io, synth  # noqa: F401
-from .engine import (Engine, DinoB200Error, device_count, load_library, quantize_gguf, LAYOUT_BGR_HWC, LAYOUT_RGB_PLANAR,  # noqa: F401
+from .engine import (Engine, Group, GATHER_CLS, GATHER_PATCH, DinoB200Error, device_count, load_library, quantize_gguf, LAYOUT_BGR_HWC, LAYOUT_RGB_PLANAR,  # noqa: F401
                      LIB_PATH)

@@ -76,6 +76,23 @@ layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, c
     layernorm_row<OUT_HALF, false, NV4>(X + off, gamma, beta, orow, D, eps, lane);
 }
 
+// Final LayerNorm fused with the feature all-gather (the one optional exchange of the data-parallel path):
+// one warp per exported token row — the class token (rows_per_image = 1) or the patch tokens (rows_per_image = NP, registers
+// stripped) of each of this rank's images — normalises the row of the residual stream (dinov2.cpp:752-761) and stores it into
+// the gather buffer of EVERY rank at [rank_slot + image][row][D]: peer stores over NVLink / NVSwitch, no separate collective,
+// no staging copy.  Visibility on the peers: kernel completion + the caller's cross-rank synchronisation.
+template <int NV4 = LN_MAX_V4>
+__global__ void __launch_bounds__(256)
+layernorm_gather_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta, GatherDst dst,
+                        int n_images, int ntok, int tok0, int rows_per_image, size_t slot_row0, int D, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_images * rows_per_image) return;
+    const int img = warp / rows_per_image, r = warp - img * rows_per_image;
+    const float *xrow = X + (static_cast<size_t>(img) * ntok + tok0 + r) * D;
+    layernorm_row_multi<NV4>(xrow, gamma, beta, dst, (slot_row0 + static_cast<size_t>(warp)) * D, D, eps, lane);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Classifier head (reference forward_head, dinov2.cpp:792-821).
 // pooled[b][d] = (sum over tokens 1..ntok-1 of Y[b][t][d]) * (1 / n_embd^2): the divisor is the constant

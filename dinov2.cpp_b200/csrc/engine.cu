@@ -27,6 +27,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <new>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -519,6 +521,18 @@ struct dino_b200_engine {
     uint8_t *d_u8 = nullptr;          // raw frames for on-device preprocessing
     size_t cap_u8 = 0;
 
+    // feature all-gather (dino_b200_gather_*): this engine is rank `g_rank` of `g_world`; g_peer[r] = rank r's gather buffer
+    // ([g_world * g_max_batch][g_rpi][D] fp32) as addressable from this device (own allocation, same-process peer, or CUDA IPC)
+    int g_rank = 0, g_world = 0, g_what = 0, g_max_batch = 0, g_rpi = 0, g_H = 0, g_W = 0;
+    float *g_buf = nullptr;
+    float *g_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool g_ipc[8] = {false, false, false, false, false, false, false, false};
+    // raw-frame slots of the pipelined uint8 interface (dino_b200_submit_u8) and their PCA colour results
+    uint8_t *d_u8s[2] = {nullptr, nullptr};
+    size_t cap_u8s[2] = {0, 0};
+    uint8_t *r_rgb[2] = {nullptr, nullptr};
+    size_t cap_rgb[2] = {0, 0};
+
     uint64_t launches = 0;
     bool profiling = false;
     std::vector<ProfileEvent> prof;
@@ -748,6 +762,7 @@ static void build_engine(dino_b200_engine *e, const dino_b200_model_desc *desc) 
 
 // ------------------------------------------------------------------------------------------------ arena
 static void drop_graphs(dino_b200_engine *e);
+static void gather_release(dino_b200_engine *e);
 static void free_arena(dino_b200_engine *e) {
     drop_graphs(e);                                         // captured forwards hold arena pointers
     void *ptrs[] = {e->d_img, e->X, e->Y, e->feat, e->logits, e->probs, e->Ape, e->Xn, e->QKV, e->AO, e->H1, e->o_cls, e->o_patch, e->ln_count};
@@ -832,6 +847,8 @@ struct Prof {
         DINO_CUDA(cudaEventRecord(e->prof.back().b, st));
     }
 };
+
+constexpr int kFlagGather = 0x100;   // internal forward flag: run the fused final-LayerNorm + all-gather kernel (engine gather state)
 
 static void drop_graphs(dino_b200_engine *e) {
     for (auto &kv : e->graphs)
@@ -959,6 +976,27 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
             prof.end();
         }
         nl += 5;
+    }
+
+    // 3a. feature all-gather fused with the final LayerNorm: exported rows go straight into every rank's gather buffer
+    if (flags & kFlagGather) {
+        prof.begin(2);
+        GatherDst dst{};
+        dst.n = e->g_world;
+        for (int r = 0; r < e->g_world; ++r) dst.p[r] = e->g_peer[r];
+        const int rpi = e->g_rpi, tok0 = e->g_what == DINO_B200_GATHER_CLS ? 0 : 1 + R;
+        const long long warps = static_cast<long long>(B) * rpi;
+        const int grid = static_cast<int>((warps * 32 + 255) / 256);
+        const size_t slot_row0 = static_cast<size_t>(e->g_rank) * e->g_max_batch * rpi;
+        const int nv4 = (D + 127) / 128;
+        if (nv4 <= 3) layernorm_gather_kernel<3><<<grid, 256, 0, st>>>(e->X, e->lnf_g, e->lnf_b, dst, B, ntok, tok0, rpi, slot_row0, D, hp.eps);
+        else if (nv4 <= 6) layernorm_gather_kernel<6><<<grid, 256, 0, st>>>(e->X, e->lnf_g, e->lnf_b, dst, B, ntok, tok0, rpi, slot_row0, D, hp.eps);
+        else if (nv4 <= 8) layernorm_gather_kernel<8><<<grid, 256, 0, st>>>(e->X, e->lnf_g, e->lnf_b, dst, B, ntok, tok0, rpi, slot_row0, D, hp.eps);
+        else layernorm_gather_kernel<12><<<grid, 256, 0, st>>>(e->X, e->lnf_g, e->lnf_b, dst, B, ntok, tok0, rpi, slot_row0, D, hp.eps);
+        DINO_CUDA(cudaGetLastError());
+        nl++;
+        prof.end();
+        if (!cls && !patch && !classify) return nl;        // nothing wanted locally: the stand-alone final LayerNorm is skipped
     }
 
     // 3. final LayerNorm (all tokens: the head pools over registers too) + outputs
@@ -1232,6 +1270,11 @@ void dino_b200_destroy(dino_b200_engine *e) {
     dino::free_arena(e);
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_u8) cudaFree(e->d_u8);
+    dino::gather_release(e);
+    for (int i = 0; i < 2; ++i) {
+        if (e->d_u8s[i]) cudaFree(e->d_u8s[i]);
+        if (e->r_rgb[i]) cudaFree(e->r_rgb[i]);
+    }
     for (void *q : {static_cast<void *>(e->pca_mean), static_cast<void *>(e->pca_v), static_cast<void *>(e->pca_w), static_cast<void *>(e->pca_y),
                     static_cast<void *>(e->pca_x), static_cast<void *>(e->pca_rgb)})
         if (q) cudaFree(q);
@@ -1628,10 +1671,10 @@ dino_b200_status dino_b200_kernel_layernorm(const float *X, const float *gamma, 
 }  // extern "C"
 
 namespace dino {
-// runs the preprocessing kernel: frames already in e->d_u8, result in e->d_img; returns output size
-static void preprocess_device(dino_b200_engine *e, int B, int H, int W, bool classify, int &OH, int &OW) {
+// output size of dino_preprocess / dino_classify_preprocess for an H x W frame (reference dinov2.cpp:106-156)
+static void preprocess_size(const dino_b200_engine *e, int H, int W, bool classify, int &RH, int &RW, int &OH, int &OW, int &cy, int &cx) {
     const int ps = e->hp.patch_size;
-    int RH, RW, cy = 0, cx = 0;
+    cy = cx = 0;
     if (classify) {
         RH = RW = 256;
         OH = OW = 224;
@@ -1643,15 +1686,26 @@ static void preprocess_device(dino_b200_engine *e, int B, int H, int W, bool cla
         OH = RH;
         OW = RW;
     }
-    ensure_arena(e, B, OH, OW);
+}
+// runs the preprocessing kernel: raw frames at src (device), float32 BGR [B][OH][OW][3] to dst (device)
+static void preprocess_launch(dino_b200_engine *e, const uint8_t *src, float *dst, int B, int H, int W, bool classify, cudaStream_t st) {
+    int RH, RW, OH, OW, cy, cx;
+    preprocess_size(e, H, W, classify, RH, RW, OH, OW, cy, cx);
     // IMAGENET mean / std are R,G,B (reference dinov2.h:16-17); the image is B,G,R
     const float3 mean = make_float3(0.406f, 0.456f, 0.485f);
     const float3 inv_std = make_float3(1.0f / 0.225f, 1.0f / 0.224f, 1.0f / 0.229f);
     const long long total = static_cast<long long>(B) * OH * OW;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(e->num_sms) * 32));
-    preprocess_bicubic_kernel<<<grid, 256, 0, e->stream>>>(e->d_u8, e->d_img, B, H, W, RH, RW, OH, OW, cy, cx, mean, inv_std);
+    preprocess_bicubic_kernel<<<grid, 256, 0, st>>>(src, dst, B, H, W, RH, RW, OH, OW, cy, cx, mean, inv_std);
     DINO_CUDA(cudaGetLastError());
     e->launches++;
+}
+// frames already in e->d_u8, result in e->d_img; returns output size
+static void preprocess_device(dino_b200_engine *e, int B, int H, int W, bool classify, int &OH, int &OW) {
+    int RH, RW, cy, cx;
+    preprocess_size(e, H, W, classify, RH, RW, OH, OW, cy, cx);
+    ensure_arena(e, B, OH, OW);
+    preprocess_launch(e, e->d_u8, e->d_img, B, H, W, classify, e->stream);
 }
 
 static void upload_frames(dino_b200_engine *e, const uint8_t *images, int B, int H, int W) {
@@ -1717,3 +1771,353 @@ extern "C" dino_b200_status dino_b200_forward_u8(dino_b200_engine *e, const uint
     DINO_API_END(e)
 }
 
+
+// ================================================================================================ pipelined raw-frame interface
+// The realtime caller's per-frame loop (reference realtime.cpp:75-101: capture -> dino_preprocess -> dino_predict -> PCA -> show)
+// as one asynchronous submission: uint8 frames in, features and / or PCA colours out, nothing but the frame and the results
+// crosses PCIe.  Shares the two-slot pipeline (and dino_b200_wait) with dino_b200_submit.
+extern "C" dino_b200_status dino_b200_submit_u8(dino_b200_engine *e, const uint8_t *frames, int B, int H, int W, int flags, float *cls,
+                                                float *patch, float *logits, float *probs, uint8_t *pca_rgb, int *out_h, int *out_w) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!frames || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit_u8: bad batch or frame size");
+    if (e->n_submitted - e->n_waited >= 2) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit_u8: two batches already in flight; call dino_b200_wait first");
+    DINO_CUDA(cudaSetDevice(e->device));
+    const int slot = static_cast<int>(e->n_submitted & 1);
+    if (!e->copy_stream) {
+        DINO_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        DINO_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_up[i], cudaEventDisableTiming));
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+            DINO_CUDA(cudaEventCreateWithFlags(&e->ev_fwd[i], cudaEventDisableTiming));
+        }
+    }
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    if (classify && !e->wc) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit_u8: checkpoint has no classifier head");
+    int RH, RW, OH, OW, cy, cx;
+    dino::preprocess_size(e, H, W, classify, RH, RW, OH, OW, cy, cx);
+    if (out_h) *out_h = OH;
+    if (out_w) *out_w = OW;
+    const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
+    const size_t np = static_cast<size_t>(OH / ps) * (OW / ps);
+    if (pca_rgb && np < 3) throw dino::StatusError(DINO_B200_ERR_INVALID, "submit_u8: PCA colouring needs at least 3 patches");
+    const size_t n_u8 = static_cast<size_t>(B) * H * W * 3, n_in = static_cast<size_t>(B) * 3 * OH * OW;
+    const bool need_patch = patch || pca_rgb;            // the PCA reads the patch tokens on the device even when the host does not want them
+    const size_t n_cls = cls ? static_cast<size_t>(B) * D : 0, n_log = (classify && logits) ? static_cast<size_t>(B) * C : 0;
+    const size_t n_prob = (classify && probs) ? static_cast<size_t>(B) * C : 0, n_patch = need_patch ? static_cast<size_t>(B) * np * D : 0;
+    const size_t n_res = n_cls + n_log + n_prob + n_patch, n_rgb = pca_rgb ? static_cast<size_t>(B) * np * 3 : 0;
+    if (n_u8 > e->cap_u8s[slot] || n_in > e->cap_in[slot] || n_res > e->cap_r[slot] || n_rgb > e->cap_rgb[slot]) {
+        DINO_CUDA(cudaStreamSynchronize(e->copy_stream));
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+        DINO_CUDA(cudaStreamSynchronize(e->d2h_stream));
+        auto grow = [&](void **ptr, size_t &cap, size_t need, size_t elem) {
+            if (need <= cap) return;
+            if (*ptr) DINO_CUDA(cudaFree(*ptr));
+            *ptr = nullptr;
+            cap = 0;
+            DINO_CUDA(cudaMalloc(ptr, need * elem));
+            cap = need;
+        };
+        grow(reinterpret_cast<void **>(&e->d_u8s[slot]), e->cap_u8s[slot], n_u8, 1);
+        grow(reinterpret_cast<void **>(&e->d_in[slot]), e->cap_in[slot], n_in, sizeof(float));
+        grow(reinterpret_cast<void **>(&e->r_buf[slot]), e->cap_r[slot], n_res, sizeof(float));
+        grow(reinterpret_cast<void **>(&e->r_rgb[slot]), e->cap_rgb[slot], n_rgb, 1);
+    }
+    dino::ensure_arena(e, B, OH, OW);
+    if (pca_rgb) dino::pca_reserve(e, B, static_cast<int>(np), false);
+    float *r_cls = e->r_buf[slot], *r_log = r_cls + n_cls, *r_prob = r_log + n_log, *r_patch = r_prob + n_prob;
+    cudaStream_t st = e->stream;
+    if (e->n_submitted >= 2) {
+        DINO_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+        DINO_CUDA(cudaStreamWaitEvent(st, e->ev_done[slot], 0));
+    }
+    DINO_CUDA(cudaMemcpyAsync(e->d_u8s[slot], frames, n_u8, cudaMemcpyHostToDevice, e->copy_stream));
+    DINO_CUDA(cudaEventRecord(e->ev_up[slot], e->copy_stream));
+    DINO_CUDA(cudaStreamWaitEvent(st, e->ev_up[slot], 0));
+    dino::preprocess_launch(e, e->d_u8s[slot], e->d_in[slot], B, H, W, classify, st);
+    dino::forward_device(e, e->d_in[slot], DINO_B200_LAYOUT_BGR_HWC, B, OH, OW, flags & DINO_B200_CLASSIFY, n_cls ? r_cls : nullptr,
+                         n_patch ? r_patch : nullptr, n_log ? r_log : nullptr, n_prob ? r_prob : nullptr, st);
+    if (pca_rgb) dino::pca_device(e, r_patch, B, static_cast<int>(np), e->r_rgb[slot], nullptr, st);
+    DINO_CUDA(cudaEventRecord(e->ev_fwd[slot], st));
+    DINO_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->ev_fwd[slot], 0));
+    if (n_cls) DINO_CUDA(cudaMemcpyAsync(cls, r_cls, n_cls * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (patch) DINO_CUDA(cudaMemcpyAsync(patch, r_patch, n_patch * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_log) DINO_CUDA(cudaMemcpyAsync(logits, r_log, n_log * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_prob) DINO_CUDA(cudaMemcpyAsync(probs, r_prob, n_prob * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (n_rgb) DINO_CUDA(cudaMemcpyAsync(pca_rgb, e->r_rgb[slot], n_rgb, cudaMemcpyDeviceToHost, e->d2h_stream));
+    DINO_CUDA(cudaEventRecord(e->ev_done[slot], e->d2h_stream));
+    e->n_submitted++;
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+// ================================================================================================ feature all-gather
+// SURVEY.md 8e / BASELINE north_star: the data-parallel path has exactly one optional exchange — every rank ends up with the
+// [cls] or patch embeddings of the WHOLE global batch.  Here it is not a separate collective: the final LayerNorm kernel of
+// each rank stores its rows directly into every rank's gather buffer (peer memory over NVLink / NVSwitch).
+namespace dino {
+static void gather_release(dino_b200_engine *e) {
+    for (int r = 0; r < 8; ++r) {
+        if (e->g_ipc[r] && e->g_peer[r]) cudaIpcCloseMemHandle(e->g_peer[r]);
+        e->g_peer[r] = nullptr;
+        e->g_ipc[r] = false;
+    }
+    if (e->g_buf) cudaFree(e->g_buf);
+    e->g_buf = nullptr;
+    e->g_world = 0;
+}
+}  // namespace dino
+
+extern "C" dino_b200_status dino_b200_gather_init(dino_b200_engine *e, int rank, int world, int what, int max_batch, int H, int W,
+                                                  void **local_buf, unsigned char *ipc_handle) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    const int ps = e->hp.patch_size;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || max_batch <= 0 || H < ps || W < ps || H % ps || W % ps ||
+        (what != DINO_B200_GATHER_CLS && what != DINO_B200_GATHER_PATCH))
+        throw dino::StatusError(DINO_B200_ERR_INVALID, "gather_init: bad rank / world (1..8) / batch / image size / selector");
+    DINO_CUDA(cudaSetDevice(e->device));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    dino::drop_graphs(e);
+    dino::gather_release(e);
+    e->g_rank = rank;
+    e->g_world = world;
+    e->g_what = what;
+    e->g_max_batch = max_batch;
+    e->g_H = H;
+    e->g_W = W;
+    e->g_rpi = what == DINO_B200_GATHER_CLS ? 1 : (H / ps) * (W / ps);
+    const size_t bytes = static_cast<size_t>(world) * max_batch * e->g_rpi * e->hp.hidden_size * sizeof(float);
+    DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->g_buf), bytes));
+    DINO_CUDA(cudaMemsetAsync(e->g_buf, 0, bytes, e->stream));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    e->g_peer[rank] = e->g_buf;
+    if (local_buf) *local_buf = e->g_buf;
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        DINO_CUDA(cudaIpcGetMemHandle(&h, e->g_buf));
+        static_assert(sizeof(h) == DINO_B200_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+        memcpy(ipc_handle, &h, sizeof(h));
+    }
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+extern "C" dino_b200_status dino_b200_gather_set_peer(dino_b200_engine *e, int r, void *dev_ptr, const unsigned char *ipc_handle) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (e->g_world == 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "gather_set_peer: call dino_b200_gather_init first");
+    if (r < 0 || r >= e->g_world || r == e->g_rank || (!dev_ptr && !ipc_handle))
+        throw dino::StatusError(DINO_B200_ERR_INVALID, "gather_set_peer: bad peer rank or no buffer given");
+    DINO_CUDA(cudaSetDevice(e->device));
+    DINO_CUDA(cudaStreamSynchronize(e->stream));
+    dino::drop_graphs(e);
+    if (e->g_ipc[r] && e->g_peer[r]) cudaIpcCloseMemHandle(e->g_peer[r]);
+    e->g_peer[r] = nullptr;
+    e->g_ipc[r] = false;
+    if (dev_ptr) {
+        // a buffer of another engine of THIS process: make the owning device's memory addressable from ours
+        cudaPointerAttributes at{};
+        DINO_CUDA(cudaPointerGetAttributes(&at, dev_ptr));
+        if (at.type != cudaMemoryTypeDevice) throw dino::StatusError(DINO_B200_ERR_INVALID, "gather_set_peer: not a device pointer");
+        if (at.device != e->device) {
+            int can = 0;
+            DINO_CUDA(cudaDeviceCanAccessPeer(&can, e->device, at.device));
+            if (!can) throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED, "gather_set_peer: no peer access between the two devices");
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) DINO_CUDA(pe);
+            cudaGetLastError();
+        }
+        e->g_peer[r] = static_cast<float *>(dev_ptr);
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof(h));
+        void *p = nullptr;
+        DINO_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->g_peer[r] = static_cast<float *>(p);
+        e->g_ipc[r] = true;
+    }
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+extern "C" dino_b200_status dino_b200_forward_gather_device(dino_b200_engine *e, const float *images, int layout, int B, int H, int W,
+                                                            int flags, float *cls, float *patch, float *logits, float *probs, void *stream) {
+    if (!e) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (e->g_world == 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "forward_gather: call dino_b200_gather_init first");
+    for (int r = 0; r < e->g_world; ++r)
+        if (!e->g_peer[r]) throw dino::StatusError(DINO_B200_ERR_INVALID, "forward_gather: the gather buffer of rank " + std::to_string(r) + " has not been registered");
+    if (B > e->g_max_batch || H != e->g_H || W != e->g_W)
+        throw dino::StatusError(DINO_B200_ERR_INVALID, "forward_gather: batch / image size differ from dino_b200_gather_init");
+    DINO_CUDA(cudaSetDevice(e->device));
+    dino::ensure_arena(e, B > 0 ? B : 1, H, W);
+    dino::forward_device(e, images, layout, B, H, W, (flags & DINO_B200_CLASSIFY) | dino::kFlagGather, cls, patch, logits, probs,
+                         stream ? static_cast<cudaStream_t>(stream) : e->stream);
+    return DINO_B200_OK;
+    DINO_API_END(e)
+}
+
+// ================================================================================================ engine group (one process, n GPUs)
+struct dino_b200_group {
+    std::vector<dino_b200_engine *> eng;
+    int g_what = 0, g_per = 0, g_H = 0, g_W = 0;      // gather configuration currently set up on the engines
+    std::string err;
+};
+
+extern "C" dino_b200_status dino_b200_group_create_from_gguf(const char *path, const int *devices, int n, dino_b200_group **out) {
+    if (!path || !devices || !out || n < 1 || n > 8) {
+        dino::g_last_error = "group_create: bad argument (1..8 devices)";
+        return DINO_B200_ERR_INVALID;
+    }
+    *out = nullptr;
+    dino_b200_group *g = new (std::nothrow) dino_b200_group();
+    if (!g) return DINO_B200_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        dino_b200_engine *e = nullptr;
+        const dino_b200_status st = dino_b200_create_from_gguf(path, devices[i], &e);
+        if (st != DINO_B200_OK) {
+            for (dino_b200_engine *x : g->eng) dino_b200_destroy(x);
+            delete g;
+            return st;
+        }
+        g->eng.push_back(e);
+    }
+    *out = g;
+    return DINO_B200_OK;
+}
+
+extern "C" void dino_b200_group_destroy(dino_b200_group *g) {
+    if (!g) return;
+    for (dino_b200_engine *e : g->eng) dino_b200_destroy(e);
+    delete g;
+}
+
+extern "C" int dino_b200_group_size(const dino_b200_group *g) { return g ? static_cast<int>(g->eng.size()) : 0; }
+
+extern "C" dino_b200_engine *dino_b200_group_engine(dino_b200_group *g, int i) {
+    return (g && i >= 0 && i < static_cast<int>(g->eng.size())) ? g->eng[i] : nullptr;
+}
+
+#define DINO_GROUP_END(grp)                                                 \
+    }                                                                       \
+    catch (const dino::StatusError &ex) {                                   \
+        dino::g_last_error = ex.what();                                     \
+        return ex.st;                                                       \
+    }                                                                       \
+    catch (const dino::CudaError &ex) {                                     \
+        dino::g_last_error = ex.what();                                     \
+        return DINO_B200_ERR_CUDA;                                          \
+    }                                                                       \
+    catch (const std::exception &ex) {                                      \
+        dino::g_last_error = ex.what();                                     \
+        return DINO_B200_ERR_INVALID;                                       \
+    }
+
+// Data-parallel forward over the group: the global batch is split into contiguous shards (image i -> engine i / ceil(B / n)),
+// every device uploads, computes and reads back its shard concurrently; one host thread drives all of them.
+extern "C" dino_b200_status dino_b200_group_forward(dino_b200_group *g, const float *images, int layout, int B, int H, int W, int flags,
+                                                    float *cls, float *patch, float *logits, float *probs) {
+    if (!g || g->eng.empty()) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "group_forward: bad batch or image size");
+    const int n = static_cast<int>(g->eng.size());
+    const int per = (B + n - 1) / n;
+    const bool classify = (flags & DINO_B200_CLASSIFY) != 0;
+    const size_t img_elems = static_cast<size_t>(3) * H * W;
+    for (int i = 0; i < n; ++i) {
+        dino_b200_engine *e = g->eng[i];
+        const int b0 = i * per, nb = std::min(per, B - b0);
+        if (nb <= 0) break;
+        DINO_CUDA(cudaSetDevice(e->device));
+        dino::ensure_arena(e, nb, H, W);
+        const int ps = e->hp.patch_size, D = e->hp.hidden_size, C = e->hp.num_classes;
+        const size_t np = static_cast<size_t>(H / ps) * (W / ps);
+        if (patch && static_cast<size_t>(nb) * np * D > e->cap_o_patch) {
+            DINO_CUDA(cudaStreamSynchronize(e->stream));
+            if (e->o_patch) DINO_CUDA(cudaFree(e->o_patch));
+            e->o_patch = nullptr;
+            e->cap_o_patch = 0;
+            DINO_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->o_patch), static_cast<size_t>(nb) * np * D * sizeof(float)));
+            e->cap_o_patch = static_cast<size_t>(nb) * np * D;
+        }
+        cudaStream_t st = e->stream;
+        DINO_CUDA(cudaMemcpyAsync(e->d_img, images + b0 * img_elems, nb * img_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+        dino::forward_device(e, e->d_img, layout, nb, H, W, flags & DINO_B200_CLASSIFY, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
+                             (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
+        if (cls) DINO_CUDA(cudaMemcpyAsync(cls + static_cast<size_t>(b0) * D, e->o_cls, static_cast<size_t>(nb) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (patch) DINO_CUDA(cudaMemcpyAsync(patch + static_cast<size_t>(b0) * np * D, e->o_patch, static_cast<size_t>(nb) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (classify && logits) DINO_CUDA(cudaMemcpyAsync(logits + static_cast<size_t>(b0) * C, e->logits, static_cast<size_t>(nb) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (classify && probs) DINO_CUDA(cudaMemcpyAsync(probs + static_cast<size_t>(b0) * C, e->probs, static_cast<size_t>(nb) * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < n; ++i) {
+        DINO_CUDA(cudaSetDevice(g->eng[i]->device));
+        DINO_CUDA(cudaStreamSynchronize(g->eng[i]->stream));
+    }
+    return DINO_B200_OK;
+    DINO_GROUP_END(g)
+}
+
+// Forward + all-gather of the features: afterwards EVERY device of the group holds the [cls] (what = DINO_B200_GATHER_CLS) or
+// patch (DINO_B200_GATHER_PATCH) embeddings of the whole batch in its own memory, laid out [n][ceil(B/n)][rows][D] (rank-major,
+// unused image slots of the last shard zero).  device_bufs (may be NULL) receives the n device pointers; host_out (may be NULL)
+// receives [B][rows][D] copied from the buffer of device `host_from` — any rank serves, that is the point of the gather.
+extern "C" dino_b200_status dino_b200_group_allgather_features(dino_b200_group *g, const float *images, int layout, int B, int H, int W,
+                                                               int what, float **device_bufs, float *host_out, int host_from) {
+    if (!g || g->eng.empty()) return DINO_B200_ERR_INVALID;
+    DINO_API_BEGIN
+    if (!images || B <= 0 || H <= 0 || W <= 0) throw dino::StatusError(DINO_B200_ERR_INVALID, "group_allgather: bad batch or image size");
+    const int n = static_cast<int>(g->eng.size());
+    if (host_from < 0 || host_from >= n) throw dino::StatusError(DINO_B200_ERR_INVALID, "group_allgather: host_from is not a rank of the group");
+    const int per = (B + n - 1) / n;
+    if (g->g_what != what || g->g_per < per || g->g_H != H || g->g_W != W) {
+        std::vector<void *> bufs(n, nullptr);
+        for (int i = 0; i < n; ++i) {
+            const dino_b200_status st = dino_b200_gather_init(g->eng[i], i, n, what, per, H, W, &bufs[i], nullptr);
+            if (st != DINO_B200_OK) return st;
+        }
+        for (int i = 0; i < n; ++i)
+            for (int r = 0; r < n; ++r)
+                if (r != i) {
+                    const dino_b200_status st = dino_b200_gather_set_peer(g->eng[i], r, bufs[r], nullptr);
+                    if (st != DINO_B200_OK) return st;
+                }
+        g->g_what = what;
+        g->g_per = per;
+        g->g_H = H;
+        g->g_W = W;
+    }
+    const int slot = g->g_per;                               // image slots per rank in the gather buffers
+    const size_t img_elems = static_cast<size_t>(3) * H * W;
+    for (int i = 0; i < n; ++i) {
+        dino_b200_engine *e = g->eng[i];
+        const int b0 = i * per, nb = std::min(per, B - b0);
+        if (nb <= 0) break;
+        DINO_CUDA(cudaSetDevice(e->device));
+        dino::ensure_arena(e, nb, H, W);
+        DINO_CUDA(cudaMemcpyAsync(e->d_img, images + b0 * img_elems, nb * img_elems * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        dino::forward_device(e, e->d_img, layout, nb, H, W, dino::kFlagGather, nullptr, nullptr, nullptr, nullptr, e->stream);
+    }
+    // every rank's peer stores have landed once every stream has drained
+    for (int i = 0; i < n; ++i) {
+        DINO_CUDA(cudaSetDevice(g->eng[i]->device));
+        DINO_CUDA(cudaStreamSynchronize(g->eng[i]->stream));
+    }
+    if (device_bufs)
+        for (int i = 0; i < n; ++i) device_bufs[i] = g->eng[i]->g_buf;
+    if (host_out) {
+        dino_b200_engine *e = g->eng[host_from];
+        const size_t row = static_cast<size_t>(e->g_rpi) * e->hp.hidden_size;
+        DINO_CUDA(cudaSetDevice(e->device));
+        for (int i = 0; i < n; ++i) {
+            const int b0 = i * per, nb = std::min(per, B - b0);
+            if (nb <= 0) break;
+            DINO_CUDA(cudaMemcpyAsync(host_out + static_cast<size_t>(b0) * row, e->g_buf + static_cast<size_t>(i) * slot * row,
+                                      static_cast<size_t>(nb) * row * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
+        DINO_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return DINO_B200_OK;
+    DINO_GROUP_END(g)
+}

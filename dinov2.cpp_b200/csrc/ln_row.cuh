@@ -60,4 +60,57 @@ __device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, co
     }
 }
 
+// Destinations of the fused final-LayerNorm + all-gather kernel: the same row is stored into the gather buffer of every rank
+// (peer device memory over NVLink / NVSwitch, or this device for the rank's own copy).
+struct GatherDst {
+    float *p[8];
+    int n;
+};
+
+// Same arithmetic as layernorm_row<false, ...> (bit-identical values), stored to n destinations.
+template <int NV4 = LN_MAX_V4>
+__device__ __forceinline__ void layernorm_row_multi(const float *__restrict__ xrow, const float *__restrict__ gamma,
+                                                    const float *__restrict__ beta, const GatherDst &dst, size_t dst_off, int D, float eps,
+                                                    int lane) {
+    const int nv = D >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+    float4 v[NV4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i] = x4[idx];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / static_cast<float>(D) + eps);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+            const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+            const float4 y = make_float4((v[i].x * rstd) * g.x + b.x, (v[i].y * rstd) * g.y + b.y, (v[i].z * rstd) * g.z + b.z,
+                                         (v[i].w * rstd) * g.w + b.w);
+            for (int k = 0; k < dst.n; ++k) reinterpret_cast<float4 *>(dst.p[k] + dst_off)[idx] = y;
+        }
+    }
+}
+
 }  // namespace dino

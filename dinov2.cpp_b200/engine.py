@@ -32,8 +32,14 @@ ABI_SYMBOLS = [
     "dino_b200_last_error", "dino_b200_kernel_launches", "dino_b200_set_profiling", "dino_b200_get_profile",
     "dino_b200_kernel_gemm", "dino_b200_kernel_gemm_resid_ln", "dino_b200_kernel_attention", "dino_b200_kernel_layernorm",
     "dino_b200_preprocess", "dino_b200_forward_u8", "dino_b200_submit", "dino_b200_wait",
-    "dino_b200_pca_rgb", "dino_b200_pca_rgb_device", "dino_b200_quantize_gguf",
+    "dino_b200_pca_rgb", "dino_b200_pca_rgb_device", "dino_b200_quantize_gguf", "dino_b200_submit_u8",
+    "dino_b200_gather_init", "dino_b200_gather_set_peer", "dino_b200_forward_gather_device",
+    "dino_b200_group_create_from_gguf", "dino_b200_group_destroy", "dino_b200_group_size", "dino_b200_group_engine",
+    "dino_b200_group_forward", "dino_b200_group_allgather_features",
 ]
+
+GATHER_CLS, GATHER_PATCH = 1, 2
+IPC_HANDLE_BYTES = 64
 
 
 class HParams(C.Structure):
@@ -77,6 +83,18 @@ def load_library() -> C.CDLL:
     L.dino_b200_forward_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_submit.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
     L.dino_b200_wait.argtypes = [vp]
+    L.dino_b200_submit_u8.argtypes = [vp, vp, ip, ip, ip, ip, fp, fp, fp, fp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dino_b200_gather_init.argtypes = [vp, ip, ip, ip, ip, ip, ip, C.POINTER(vp), vp]
+    L.dino_b200_gather_set_peer.argtypes = [vp, ip, vp, vp]
+    L.dino_b200_forward_gather_device.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp, vp]
+    L.dino_b200_group_create_from_gguf.argtypes = [C.c_char_p, C.POINTER(C.c_int), ip, C.POINTER(vp)]
+    L.dino_b200_group_destroy.argtypes = [vp]
+    L.dino_b200_group_destroy.restype = None
+    L.dino_b200_group_size.argtypes = [vp]
+    L.dino_b200_group_engine.argtypes = [vp, ip]
+    L.dino_b200_group_engine.restype = vp
+    L.dino_b200_group_forward.argtypes = [vp, fp, ip, ip, ip, ip, ip, fp, fp, fp, fp]
+    L.dino_b200_group_allgather_features.argtypes = [vp, fp, ip, ip, ip, ip, ip, C.POINTER(vp), fp, ip]
     L.dino_b200_quantize_gguf.argtypes = [C.c_char_p, C.c_char_p, ip]
     L.dino_b200_pca_rgb.argtypes = [vp, fp, ip, ip, vp, fp]
     L.dino_b200_pca_rgb_device.argtypes = [vp, vp, ip, ip, vp, vp, vp]
@@ -235,6 +253,39 @@ class Engine:
         """Block until the oldest submitted batch has completed."""
         _check(load_library().dino_b200_wait(self._h), self._h)
 
+    def submit_u8(self, frames_u8: np.ndarray, out: Dict[str, np.ndarray], classify: bool = False):
+        """Pipelined raw-frame path (realtime.cpp's loop): uint8 BGR frames [B,H,W,3] in; the arrays present in `out` ("cls",
+        "patch_tokens", "logits", "probs", "pca_rgb" — uint8 [B,NP,3]) are filled when the matching wait() returns.
+        Returns the preprocessed (H, W)."""
+        if frames_u8.dtype != np.uint8 or not frames_u8.flags["C_CONTIGUOUS"] or frames_u8.ndim != 4 or frames_u8.shape[3] != 3:
+            raise ValueError("submit_u8 needs a C-contiguous uint8 [B,H,W,3] array (no hidden copy may be made)")
+        B, H, W, _ = frames_u8.shape
+        oh, ow = C.c_int(), C.c_int()
+        _check(load_library().dino_b200_submit_u8(
+            self._h, frames_u8.ctypes.data, B, H, W, FLAG_CLASSIFY if classify else 0, _host_ptr(out.get("cls")),
+            _host_ptr(out.get("patch_tokens")), _host_ptr(out.get("logits")), _host_ptr(out.get("probs")),
+            _host_ptr(out.get("pca_rgb")), C.byref(oh), C.byref(ow)), self._h)
+        return oh.value, ow.value
+
+    # -- feature all-gather (one engine = one rank) -------------------------
+    def gather_init(self, rank: int, world: int, what: int, max_batch: int, H: int, W: int):
+        """Allocates this rank's gather buffer; returns (device pointer, 64-byte CUDA IPC handle)."""
+        buf = C.c_void_p()
+        handle = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        _check(load_library().dino_b200_gather_init(self._h, rank, world, what, max_batch, H, W, C.byref(buf), handle), self._h)
+        return buf.value, bytes(handle)
+
+    def gather_set_peer(self, r: int, dev_ptr: int = 0, ipc_handle: Optional[bytes] = None):
+        h = (C.c_ubyte * IPC_HANDLE_BYTES).from_buffer_copy(ipc_handle) if ipc_handle else None
+        _check(load_library().dino_b200_gather_set_peer(self._h, r, dev_ptr or None, h), self._h)
+
+    def forward_gather_device(self, images_ptr: int, layout: int, B: int, H: int, W: int, classify: bool = False, cls_ptr: int = 0,
+                              patch_ptr: int = 0, logits_ptr: int = 0, probs_ptr: int = 0, stream: int = 0):
+        """forward_device + the fused final-LayerNorm / peer-store all-gather into every registered gather buffer."""
+        _check(load_library().dino_b200_forward_gather_device(
+            self._h, images_ptr, layout, B, H, W, FLAG_CLASSIFY if classify else 0, cls_ptr or None, patch_ptr or None,
+            logits_ptr or None, probs_ptr or None, stream or None), self._h)
+
     def pca_rgb(self, patch_tokens: np.ndarray, want_proj: bool = False):
         """PCA colouring of inference.cpp:76-86 on the device: patch_tokens float32 [B, NP, D] -> uint8 [B, NP, 3]
         (and, optionally, the float projections [B, NP, 3])."""
@@ -295,6 +346,59 @@ class Engine:
         _check(load_library().dino_b200_forward_device(
             self._h, images_ptr, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
             cls_ptr or None, patch_ptr or None, logits_ptr or None, probs_ptr or None, stream or None), self._h)
+
+
+class Group:
+    """n engines on n devices of one process (dino_b200_group_*): data-parallel forward and the fused feature all-gather,
+    driven from plain C calls — no torch, no NCCL."""
+
+    def __init__(self, gguf_path: str, devices):
+        L = load_library()
+        self._g = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(L.dino_b200_group_create_from_gguf(os.fsencode(gguf_path), devs, len(devices), C.byref(self._g)))
+        self.n = int(L.dino_b200_group_size(self._g))
+        hp = HParams()
+        _check(L.dino_b200_get_hparams(L.dino_b200_group_engine(self._g, 0), C.byref(hp)))
+        self.hp = hp
+
+    def close(self):
+        if self._g:
+            load_library().dino_b200_group_destroy(self._g)
+            self._g = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def forward(self, images: np.ndarray, classify: bool = False, layout: int = LAYOUT_BGR_HWC, want_patch: bool = True) -> Dict[str, np.ndarray]:
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        B, H, W = (images.shape[0], images.shape[1], images.shape[2]) if layout == LAYOUT_BGR_HWC else (images.shape[0], images.shape[2], images.shape[3])
+        D, ps, Cn = self.hp.hidden_size, self.hp.patch_size, self.hp.num_classes
+        NP = (H // ps) * (W // ps)
+        res = {"cls": np.empty((B, D), np.float32)}
+        if want_patch:
+            res["patch_tokens"] = np.empty((B, NP, D), np.float32)
+        if classify:
+            res["logits"] = np.empty((B, Cn), np.float32)
+            res["probs"] = np.empty((B, Cn), np.float32)
+        _check(load_library().dino_b200_group_forward(self._g, images.ctypes.data, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
+                                                      _host_ptr(res.get("cls")), _host_ptr(res.get("patch_tokens")),
+                                                      _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))))
+        return res
+
+    def allgather_features(self, images: np.ndarray, what: int = GATHER_CLS, layout: int = LAYOUT_BGR_HWC, host_from: int = 0):
+        """Returns (features [B, rows, D] copied from device `host_from`, list of the n per-device gather buffer pointers)."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        B, H, W = (images.shape[0], images.shape[1], images.shape[2]) if layout == LAYOUT_BGR_HWC else (images.shape[0], images.shape[2], images.shape[3])
+        D, ps = self.hp.hidden_size, self.hp.patch_size
+        rows = 1 if what == GATHER_CLS else (H // ps) * (W // ps)
+        out = np.empty((B, rows, D), np.float32)
+        bufs = (C.c_void_p * self.n)()
+        _check(load_library().dino_b200_group_allgather_features(self._g, images.ctypes.data, layout, B, H, W, what, bufs, out.ctypes.data, host_from))
+        return out, [b for b in bufs]
 
 
 # ---- kernel-level hooks (device pointers) ---------------------------------

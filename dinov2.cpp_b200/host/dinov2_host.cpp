@@ -17,6 +17,7 @@
 // dinov2.cpp:875-876); enable_flash_attn is accepted and ignored (the engine always computes exact attention).
 #include "dinov2.h"
 #include "ggml-backend.h"
+#include "dinov2_b200_batch.h"
 
 #include <opencv2/core.hpp>
 #include <opencv2/imgproc.hpp>
@@ -50,6 +51,10 @@ struct ggml_backend_buffer_type {
 struct ggml_gallocr {
     int unused = 0;
 };
+// the key / value section of a checkpoint as get_val_u32 / get_val_str see it (reference dinov2.h:20-23)
+struct gguf_context {
+    const dino::GGUFFile *file = nullptr;
+};
 
 static dino_b200_engine *engine_of(const dino_model &model) { return model.backend ? model.backend->engine : nullptr; }
 
@@ -58,6 +63,25 @@ uint32_t dino_hparams::n_enc_head_dim() const { return hidden_size / num_attenti
 uint32_t dino_hparams::n_img_size() const { return img_size; }
 uint32_t dino_hparams::n_patch_size() const { return patch_size; }
 uint32_t dino_hparams::n_img_embd() const { return img_size / patch_size; }
+
+// get_val_u32 / get_val_str (dinov2.cpp:55-67): the reference looks the key up with gguf_find_key and reads it; a missing
+// key is a fatal invariant there (GGML_ASSERT inside gguf_get_val_*), here it aborts with the same kind of message.
+uint32_t get_val_u32(const struct gguf_context *ctx, const char *key) {
+    auto it = ctx->file->kv_u.find(key);
+    if (it == ctx->file->kv_u.end()) {
+        fprintf(stderr, "%s: key '%s' not found in the gguf\n", __func__, key);
+        abort();
+    }
+    return (uint32_t) it->second;
+}
+const char *get_val_str(const struct gguf_context *ctx, const char *key) {
+    auto it = ctx->file->kv_s.find(key);
+    if (it == ctx->file->kv_s.end()) {
+        fprintf(stderr, "%s: key '%s' not found in the gguf\n", __func__, key);
+        abort();
+    }
+    return it->second.c_str();
+}
 
 bool do_quantize(const char *name, const struct ggml_tensor *tensor) {
     // 2-D tensors whose name ends in "weight" (reference PATTERN ".*weight", dinov2.h:18 / dinov2.cpp:227-236)
@@ -81,13 +105,13 @@ bool dino_model_load(const cv::Size img_size, const std::string &fname, dino_mod
         delete ctx;
         return false;
     }
+    const gguf_context kv{&ctx->file};
     auto u32 = [&](const char *k, uint32_t &dst) {
-        auto it = ctx->file.kv_u.find(k);
-        if (it == ctx->file.kv_u.end()) {
+        if (!ctx->file.kv_u.count(k)) {
             fprintf(stderr, "%s: key '%s' missing from gguf\n", __func__, k);
             return false;
         }
-        dst = (uint32_t) it->second;
+        dst = get_val_u32(&kv, k);
         return true;
     };
     auto &hp = model.hparams;
@@ -117,20 +141,22 @@ bool dino_model_load(const cv::Size img_size, const std::string &fname, dino_mod
             hp.id2label[(int) i] = it == ctx->file.kv_s.end() ? std::string() : it->second;
         }
     } else {
-        uint32_t nc = 0;
-        hp.num_classes = u32("num_classes", nc) ? nc : 0;
+        hp.num_classes = 0;          // as the reference: the key is only read for -c (dinov2.cpp:297-304)
     }
     hp.ftype %= 1000;
 
     // model.tensors: one ggml_tensor per checkpoint tensor, data pointing at the host copy
-    std::vector<dino_b200_tensor> table(ctx->file.tensors.size());
-    for (size_t i = 0; i < table.size(); ++i) {
+    // bytes per block of each ggml type (ggml_type_size): F32, F16, Q4_0, Q4_1, -, -, Q5_0, Q5_1, Q8_0
+    static const size_t kTypeSize[9] = {4, 2, 18, 20, 0, 0, 22, 24, 34};
+    std::vector<dino_b200_tensor> table;
+    table.reserve(ctx->file.tensors.size());
+    for (size_t i = 0; i < ctx->file.tensors.size(); ++i) {
         const auto &t = ctx->file.tensors[i];
         auto *gt = new ggml_tensor();
         std::memset(gt, 0, sizeof(*gt));
         gt->type = (ggml_type) t.type;
         for (int d = 0; d < 4; ++d) gt->ne[d] = t.ne[d];
-        gt->nb[0] = t.type == 0 ? 4 : (t.type == 1 ? 2 : 34);
+        gt->nb[0] = (t.type >= 0 && t.type < 9) ? kTypeSize[t.type] : 0;      // ggml: nb[0] = type size, nb[1] = nb[0] * ne[0] / block
         gt->nb[1] = t.nbytes / std::max<int64_t>(1, t.ne[1] * t.ne[2] * t.ne[3]);
         gt->nb[2] = gt->nb[1] * t.ne[1];
         gt->nb[3] = gt->nb[2] * t.ne[2];
@@ -138,7 +164,9 @@ bool dino_model_load(const cv::Size img_size, const std::string &fname, dino_mod
         std::snprintf(gt->name, sizeof(gt->name), "%s", t.name.c_str());
         ctx->tensors.push_back(gt);
         model.tensors[t.name] = gt;
-        table[i] = dino_b200_tensor{t.name.c_str(), t.type, t.n_dims, {t.ne[0], t.ne[1], t.ne[2], t.ne[3]}, t.data, t.nbytes};
+        // the engine uploads the classifier head only when the model is loaded for classification (model.tensors lists it either way)
+        if (!params.classify && t.name.rfind("classifier.", 0) == 0) continue;
+        table.push_back(dino_b200_tensor{t.name.c_str(), t.type, t.n_dims, {t.ne[0], t.ne[1], t.ne[2], t.ne[3]}, t.data, t.nbytes});
     }
     dino_b200_model_desc desc{};
     desc.hparams = dino_b200_hparams{hp.hidden_size, hp.num_hidden_layers, hp.num_attention_heads, hp.num_classes,
@@ -259,6 +287,59 @@ std::unique_ptr<dino_output> dino_predict(const dino_model &model, const cv::Mat
         output->patch_tokens = patch_tokens;
     }
     return output;
+}
+
+// Batched dino_predict (new surface: the reference is batch 1, dinov2.cpp:630): B preprocessed images of one size in, one
+// dino_output per image out, ONE forward pass on the device.  Same per-image semantics as dino_predict (top-k printed and
+// returned for -c, patch tokens otherwise).
+std::vector<std::unique_ptr<dino_output>> dino_predict_batch(const dino_model &model, const std::vector<cv::Mat> &imgs, const dino_params &params) {
+    std::vector<std::unique_ptr<dino_output>> outs;
+    dino_b200_engine *eng = engine_of(model);
+    if (!eng || imgs.empty()) {
+        fprintf(stderr, "%s: no engine or empty batch\n", __func__);
+        return outs;
+    }
+    const auto &hp = model.hparams;
+    const int ps = (int) hp.patch_size, B = (int) imgs.size();
+    const int H = imgs[0].rows / ps * ps, W = imgs[0].cols / ps * ps;
+    std::vector<float> packed((size_t) B * H * W * 3);
+    for (int b = 0; b < B; ++b) {
+        const cv::Mat &im = imgs[b];
+        if (im.type() != CV_32FC3 || im.rows != imgs[0].rows || im.cols != imgs[0].cols) {
+            fprintf(stderr, "%s: every image must be CV_32FC3 and of the same size\n", __func__);
+            return outs;
+        }
+        for (int y = 0; y < H; ++y) std::memcpy(&packed[((size_t) b * H + y) * W * 3], im.ptr<float>(y), (size_t) W * 3 * sizeof(float));
+    }
+    const int np = (H / ps) * (W / ps), D = (int) hp.hidden_size, C = (int) hp.num_classes;
+    std::vector<float> probs(params.classify ? (size_t) B * C : 0), patch(params.classify ? 0 : (size_t) B * np * D);
+    if (dino_b200_forward(eng, packed.data(), DINO_B200_LAYOUT_BGR_HWC, B, H, W, params.classify ? DINO_B200_CLASSIFY : 0, nullptr,
+                          params.classify ? nullptr : patch.data(), nullptr, params.classify ? probs.data() : nullptr) != DINO_B200_OK) {
+        fprintf(stderr, "%s: dino_b200_forward() failed: %s\n", __func__, dino_b200_last_error(eng));
+        return outs;
+    }
+    for (int b = 0; b < B; ++b) {
+        auto o = std::make_unique<dino_output>();
+        if (params.classify) {
+            const float *p = &probs[(size_t) b * C];
+            std::vector<int> order(C);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return p[x] > p[y]; });
+            std::vector<uint32_t> preds(params.topk);
+            for (uint32_t i = 0; i < params.topk && i < order.size(); ++i) {
+                auto it = hp.id2label.find(order[i]);
+                printf(" [%d] > %s : %.2f\n", b, it == hp.id2label.end() ? "?" : it->second.c_str(), p[order[i]]);
+                preds[i] = (uint32_t) order[i];
+            }
+            o->preds = preds;
+        } else {
+            cv::Mat pt(np, D, CV_32F);
+            std::memcpy(pt.data, &patch[(size_t) b * np * D], (size_t) np * D * sizeof(float));
+            o->patch_tokens = pt;
+        }
+        outs.push_back(std::move(o));
+    }
+    return outs;
 }
 
 // ------------------------------------------------------------------------------------------------ CLI helpers

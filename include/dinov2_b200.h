@@ -9,8 +9,8 @@
  * dino_predict ..., reference dinov2.h:94-118) on top of these calls is dinov2.cpp_b200/host/; the
  * binding a reference maintainer would add is shown in INTEGRATION.md.
  *
- * Threading: one engine per device, one in-flight forward per engine (the reference is single-caller too:
- * dino_predict rebuilds its graph and shares one allocator, dinov2.cpp:907-910).
+ * Threading: any number of engines per process, on one or several devices; one caller at a time per engine (the reference
+ * is single-caller too: dino_predict rebuilds its graph and shares one allocator, dinov2.cpp:907-910).
  */
 #ifndef DINOV2_B200_H
 #define DINOV2_B200_H
@@ -143,6 +143,16 @@ DINO_B200_API dino_b200_status dino_b200_submit(dino_b200_engine *e, const float
                                                 int flags, float *cls, float *patch, float *logits, float *probs);
 DINO_B200_API dino_b200_status dino_b200_wait(dino_b200_engine *e);
 
+/* The realtime caller's whole per-frame loop (reference realtime.cpp:75-101: VideoCapture -> dino_preprocess -> dino_predict ->
+ * cv::PCA colouring -> imshow) as ONE asynchronous submission on raw frames: uint8 BGR [B][H][W][3] in host memory (pinned for
+ * real overlap) -> upload -> device preprocessing (as dino_b200_preprocess; mode follows DINO_B200_CLASSIFY) -> forward ->
+ * optional PCA colouring (as dino_b200_pca_rgb: pca_rgb [B][NP][3] uint8, may be NULL) -> read-back.  Only the frame and the
+ * requested results cross PCIe.  Shares the two-slot pipeline of dino_b200_submit: complete each submission with
+ * dino_b200_wait.  out_h / out_w (may be NULL) receive the preprocessed size; NP = (out_h / ps) * (out_w / ps). */
+DINO_B200_API dino_b200_status dino_b200_submit_u8(dino_b200_engine *e, const uint8_t *frames, int B, int H, int W, int flags,
+                                                   float *cls, float *patch, float *logits, float *probs, uint8_t *pca_rgb,
+                                                   int *out_h, int *out_w);
+
 /* "Next row" of the hot path: the reference's host-side OpenCV preprocessing on the device.
  * images: B raw frames, uint8 BGR interleaved [B][H][W][3] in HOST memory (what cv::imread / VideoCapture deliver).
  * classify == 0 replaces dino_preprocess (dinov2.cpp:135-156): x/255, bicubic resize UP to the next patch multiple
@@ -174,6 +184,46 @@ DINO_B200_API dino_b200_status dino_b200_pca_rgb_device(dino_b200_engine *e, con
  * Re-encodes every 2-D "*weight" tensor of a F16/F32 gguf as ggml_type 2 (q4_0), 3 (q4_1), 6 (q5_0), 7 (q5_1) or 8 (q8_0)
  * with the reference's deterministic quantisers and writes the file the reference tool would write. */
 DINO_B200_API dino_b200_status dino_b200_quantize_gguf(const char *fname_inp, const char *fname_out, int ggml_type);
+
+/* ---- multi-GPU data parallelism from C / C++ (the "allgather_features over engines[]" entry) ----
+ * Images are independent: weights are replicated, the batch is sharded, and the ONLY exchange is the optional all-gather of the
+ * per-image features (class token or patch tokens).  It is fused into the last kernel of the forward pass: the final LayerNorm
+ * of every rank stores its rows straight into the gather buffer of every rank (peer memory over NVLink / NVSwitch), so there is
+ * no separate collective and no staging copy.  The reference has no counterpart (batch 1, one device: dinov2.cpp:630).
+ *
+ * Low level (one engine = one rank; works across processes through CUDA IPC handles, or inside one process):
+ *   gather_init      allocates this rank's gather buffer [world * max_batch][rows][D] fp32 (rows = 1 for DINO_B200_GATHER_CLS,
+ *                    NP for DINO_B200_GATHER_PATCH at H x W) and returns its device pointer and/or a 64-byte cudaIpcMemHandle_t
+ *   gather_set_peer  registers rank r's buffer: a device pointer of the same process (peer access is enabled) OR an IPC handle
+ *   forward_gather_device   dino_b200_forward_device + the fused final-LayerNorm / peer-store all-gather: this rank's rows land
+ *                    in slot [rank * max_batch + image] of EVERY registered buffer.  Asynchronous; the rows of the other ranks
+ *                    are complete in the local buffer once every rank's stream has been synchronised (caller's barrier).
+ *                    cls / patch / logits / probs (device, may be NULL) are the usual local outputs. */
+enum { DINO_B200_GATHER_CLS = 1, DINO_B200_GATHER_PATCH = 2 };
+#define DINO_B200_IPC_HANDLE_BYTES 64
+DINO_B200_API dino_b200_status dino_b200_gather_init(dino_b200_engine *e, int rank, int world, int what, int max_batch, int H, int W,
+                                                     void **local_buf, unsigned char *ipc_handle);
+DINO_B200_API dino_b200_status dino_b200_gather_set_peer(dino_b200_engine *e, int r, void *dev_ptr, const unsigned char *ipc_handle);
+DINO_B200_API dino_b200_status dino_b200_forward_gather_device(dino_b200_engine *e, const float *images, int layout, int B, int H,
+                                                               int W, int flags, float *cls, float *patch, float *logits,
+                                                               float *probs, void *stream);
+
+/* High level: n engines on n devices of ONE process (the host code stays C / C++, no torch, no NCCL).
+ *   group_forward             dino_b200_forward over a global batch: image i runs on engine i / ceil(B / n); uploads, forward
+ *                             passes and read-backs of all devices overlap; host in, host out (pin the buffers for real overlap)
+ *   group_allgather_features  forward + fused all-gather: every device ends up with the features of the WHOLE batch, laid out
+ *                             [n][ceil(B/n)][rows][D]; device_bufs (NULL or n pointers) receives the per-device buffers,
+ *                             host_out (NULL or [B][rows][D]) a copy taken from device `host_from` */
+typedef struct dino_b200_group dino_b200_group;
+DINO_B200_API dino_b200_status dino_b200_group_create_from_gguf(const char *path, const int *devices, int n, dino_b200_group **out);
+DINO_B200_API void dino_b200_group_destroy(dino_b200_group *g);
+DINO_B200_API int dino_b200_group_size(const dino_b200_group *g);
+DINO_B200_API dino_b200_engine *dino_b200_group_engine(dino_b200_group *g, int i);
+DINO_B200_API dino_b200_status dino_b200_group_forward(dino_b200_group *g, const float *images, int layout, int B, int H, int W,
+                                                       int flags, float *cls, float *patch, float *logits, float *probs);
+DINO_B200_API dino_b200_status dino_b200_group_allgather_features(dino_b200_group *g, const float *images, int layout, int B, int H,
+                                                                  int W, int what, float **device_bufs, float *host_out,
+                                                                  int host_from);
 
 /* Replaces ggml_backend_synchronize (inference.cpp:62,66). */
 DINO_B200_API dino_b200_status dino_b200_synchronize(dino_b200_engine *e);

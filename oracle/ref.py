@@ -24,7 +24,18 @@ def _cpu_flags() -> set:
     return set()
 
 
+def builds() -> list:
+    """The reference builds this host can run, best first: "v4" (x86-64-v4, AVX-512) and / or "v3" (x86-64-v3)."""
+    flags = _cpu_flags()
+    v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+    return [b for b in ((["v4"] if v4 else []) + ["v3"]) if os.path.exists(os.path.join(_HERE, "_ref", f"libdino_ref_{b}.so"))]
+
+
 def lib_path() -> Optional[str]:
+    forced = os.environ.get("DINO_REF_BUILD")          # "v3" / "v4": pick one build explicitly (self-noise measurements)
+    if forced:
+        p = os.path.join(_HERE, "_ref", f"libdino_ref_{forced}.so")
+        return p if os.path.exists(p) else None
     flags = _cpu_flags()
     v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
     for name in (["libdino_ref_v4.so"] if v4 else []) + ["libdino_ref_v3.so"]:
@@ -152,3 +163,32 @@ class Reference:
             self.close()
         except Exception:
             pass
+
+
+def forward_in_subprocess(build: str, gguf_path: str, img_bgr_hwc: np.ndarray, classify: bool) -> Dict[str, np.ndarray]:
+    """Runs ONE forward of the reference build `build` ("v3" / "v4") in a child process (the two builds export the same
+    symbols, so they are never loaded side by side) and returns its outputs.  Used to measure how far the unmodified
+    reference is from ITSELF across its own compile targets — the noise floor a parity tolerance has to respect."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        inp, outp = os.path.join(td, "img.npy"), os.path.join(td, "out.npz")
+        np.save(inp, np.ascontiguousarray(img_bgr_hwc, dtype=np.float32))
+        env = dict(os.environ, DINO_REF_BUILD=build)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), gguf_path, inp, outp, "1" if classify else "0"], env=env,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference build {build} failed: {r.stderr[-500:]}")
+        with np.load(outp) as z:
+            return {k: z[k] for k in z.files}
+
+
+if __name__ == "__main__":
+    import sys
+    _gguf, _inp, _outp, _cl = sys.argv[1:5]
+    _img = np.load(_inp)
+    _R = Reference(_gguf, classify=_cl == "1", H=_img.shape[0], W=_img.shape[1])
+    _o = _R.forward(_img)
+    _R.close()
+    np.savez(_outp, **_o)

@@ -228,3 +228,149 @@ def test_pipelined_submit_wait_matches_synchronous_forward(workdir):
         for k in range(len(batches)):
             for name in want[k]:
                 assert np.array_equal(outs[k][name], want[k][name]), (k, name)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size parity on every BASELINE.json config, against the reference itself (oracle/_ref: the unmodified reference
+# built from /root/reference, running live on this box's host cores).  The engine runs the WHOLE batch of the config;
+# the reference (batch 1 only, dinov2.cpp:630) re-computes the first and the last image of that batch.
+# ---------------------------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not refmod.available(), reason="oracle/_ref (the reference build) did not travel to this box")
+
+
+def _report(tag, got, want):
+    e = np.abs(got - want)
+    inside = float((e <= 1e-3 + 1e-3 * np.abs(want)).mean())
+    print(f"[parity] {tag}: nmse {nmse(got, want):.3e} max_abs {float(e.max()):.3e} inside(1e-3+1e-3|ref|) {inside:.5f}")
+    return inside
+
+
+@needs_ref
+def test_vitb14_b64_features_vs_reference(workdir):
+    """BASELINE.json configs[2]: ViT-B/14, batch 64, feature extraction — patch tokens and cls of images 0 and 63
+    (image 63 sits in the last wave of every kernel's tile schedule).  The reference's own noise floor on this checkpoint
+    (numpy restatement vs reference build, image 0): NMSE 2.2e-7, max_abs 2.6e-3, 99.49 % of the elements inside
+    1e-3 + 1e-3 |ref| — the 99.9 % of SURVEY.md appendix D is a ViT-S figure, so the fraction is gated at 99 % here."""
+    p = os.path.join(workdir, "vitb14.gguf")
+    synth.write_synth_gguf(p, synth.CONFIGS["vitb14"], seed=0)
+    imgs = synth.lcg_batch(100, 64, 518, 518)
+    with d.Engine(p) as e:
+        out = e.forward(imgs, classify=False)
+    assert np.isfinite(out["patch_tokens"]).all()
+    R = refmod.Reference(p, classify=False, H=518, W=518)
+    for i in (0, 63):
+        o = R.forward(imgs[i])
+        inside = _report(f"vitb14 b64 image {i} patch", out["patch_tokens"][i], o["patch_tokens"])
+        assert nmse(out["patch_tokens"][i], o["patch_tokens"]) < NMSE_F16
+        assert np.abs(out["patch_tokens"][i] - o["patch_tokens"]).max() < MAXABS_F16
+        assert inside > 0.99
+        assert nmse(out["cls"][i], o["cls"]) < NMSE_F16
+    R.close()
+
+
+@needs_ref
+def test_vitl14_b64_classify_vs_reference(workdir):
+    """BASELINE.json configs[3], the headline: ViT-L/14, batch 64, classify — logits, probabilities, top-1, cls and patch
+    tokens of images 0 and 63 of the full batch."""
+    p = os.path.join(workdir, "vitl14.gguf")
+    if not os.path.exists(p):
+        synth.write_synth_gguf(p, synth.CONFIGS["vitl14"], seed=0)
+    imgs = synth.lcg_batch(200, 64, 518, 518)
+    with d.Engine(p) as e:
+        out = e.forward(imgs, classify=True)
+    assert np.isfinite(out["patch_tokens"]).all() and np.isfinite(out["logits"]).all()
+    # Two reference graphs: the classify graph for logits / probabilities, the features graph for the tokens.  (Reading the
+    # final-LayerNorm tokens back out of the reference's CLASSIFY graph is not reliable: they are an intermediate there and
+    # ggml's graph allocator re-uses the first row for the pooled vector — restatement and engine agree with each other on
+    # that row and disagree with the harness by up to 3.6.)
+    Rc = refmod.Reference(p, classify=True, H=518, W=518)
+    Rf = refmod.Reference(p, classify=False, H=518, W=518)
+    for i in (0, 63):
+        o = Rc.forward(imgs[i])
+        f = Rf.forward(imgs[i])
+        _report(f"vitl14 b64 image {i} logits", out["logits"][i], o["logits"])
+        inside = _report(f"vitl14 b64 image {i} patch", out["patch_tokens"][i], f["patch_tokens"])
+        assert int(out["probs"][i].argmax()) == int(o["probs"].argmax())
+        assert nmse(out["logits"][i], o["logits"]) < NMSE_F16
+        assert nmse(out["probs"][i], o["probs"]) < NMSE_F16
+        assert nmse(out["patch_tokens"][i], f["patch_tokens"]) < NMSE_F16
+        assert np.abs(out["patch_tokens"][i] - f["patch_tokens"]).max() < MAXABS_F16
+        assert inside > 0.98     # the reference's own floor at this depth (restatement vs build, image 0): 98.8 %, NMSE 2.4e-7
+        assert nmse(out["cls"][i], f["cls"]) < NMSE_F16
+    Rc.close()
+    Rf.close()
+
+
+@needs_ref
+def test_vitg14_q8_0_b16_classify_vs_reference(workdir):
+    """BASELINE.json configs[4]: ViT-g/14 (1536 wide, 40 layers, SwiGLU) from a q8_0 checkpoint, batch 16 — the reference
+    runs its int8 x int8 path (ggml-cpu-quants.c:3597), the engine dequantises the weights once and keeps fp16 activations.
+
+    Tolerance: at this depth the int8 re-quantisation of every activation row amplifies last-bit differences, and the
+    UNMODIFIED reference no longer agrees with itself: its x86-64-v3 and x86-64-v4 builds (same sources, same flags except
+    the ISA level) differ by NMSE 8.7e-3 on the logits and 7.9e-3 on the patch tokens of image 0 (measured; the faithful
+    numpy restatement differs from either by the same amount), with equal top-1.  The 1.5e-4 bound of SURVEY.md appendix D is
+    a 12-layer ViT-S figure.  So the gate here is the reference's own spread: the engine must be no further from the reference
+    than TWICE the distance between the reference's two builds (measured live when both run on this host, else the recorded
+    8.7e-3), and top-1 must be equal.  Measured engine distance: 1.1e-2 (logits), 9.4e-3 (patch tokens)."""
+    p = os.path.join(workdir, "vitg14_q8_0.gguf")
+    synth.write_synth_gguf(p, synth.CONFIGS["vitg14"], seed=0, quant="q8_0")
+    imgs = synth.lcg_batch(300, 16, 518, 518)
+    with d.Engine(p) as e:
+        assert e.ftype == 8
+        out = e.forward(imgs, classify=True)
+    assert np.isfinite(out["logits"]).all()
+    floor_logits, floor_patch = 8.7e-3, 7.9e-3
+    if len(refmod.builds()) >= 2:
+        a = refmod.forward_in_subprocess("v3", p, imgs[0], True)
+        b = refmod.forward_in_subprocess("v4", p, imgs[0], True)
+        floor_logits, floor_patch = nmse(a["logits"], b["logits"]), nmse(a["patch_tokens"][1:], b["patch_tokens"][1:])
+        assert int(a["probs"].argmax()) == int(b["probs"].argmax())
+        print(f"[parity] vitg14 q8_0: reference v3 build vs v4 build: logits nmse {floor_logits:.3e}, patch nmse {floor_patch:.3e}")
+    R = refmod.Reference(p, classify=True, H=518, W=518)
+    for i in (0, 15):
+        o = R.forward(imgs[i])
+        _report(f"vitg14 q8_0 b16 image {i} logits", out["logits"][i], o["logits"])
+        # (tokens read from the classify graph: row 0 is recycled by ggml's allocator, see the ViT-L test)
+        _report(f"vitg14 q8_0 b16 image {i} patch", out["patch_tokens"][i][1:], o["patch_tokens"][1:])
+        assert int(out["probs"][i].argmax()) == int(o["probs"].argmax())
+        assert nmse(out["patch_tokens"][i][1:], o["patch_tokens"][1:]) < max(NMSE_Q8, 2 * floor_patch)
+        assert nmse(out["logits"][i], o["logits"]) < max(NMSE_Q8, 2 * floor_logits)
+    R.close()
+
+
+@pytest.mark.parametrize("name,classify", [("vits14", False), ("vits14", True)])
+def test_outlier_weights_vits14(name, classify, workdir):
+    """"Massive activation" statistics (synth.make_tensors(outliers=True): LayerNorm gains 8-12x larger in four channels and
+    LayerScale factors 8-12x larger in four other channels of every block; outputs reach |y| ~ 14 against a mean of 0.67).
+    This stresses exactly what the engine keeps narrower than the reference — fp16 LN output / QKV / MLP hidden buffers and
+    the fp16 operands of Q K^T and P V (reference: f32, dinov2.cpp:527-543).  NMSE and top-1 gates as for the benign
+    weights; the reference's own noise floor on this checkpoint (numpy restatement vs reference build) is NMSE 2e-7,
+    max_abs 1.8e-2, so max_abs is reported, not gated.  (With register tokens, or with both factors in the same channels,
+    the reference stops agreeing with itself — restatement vs build NMSE 1e-4 .. 4e-2 — and no parity statement is possible.)"""
+    p = os.path.join(workdir, name + "_outliers.gguf")
+    synth.write_synth_gguf(p, synth.CONFIGS[name], seed=2, outliers=True)
+    imgs = synth.lcg_batch(40, 2, 518, 518)
+    with d.Engine(p) as e:
+        out = e.forward(imgs, classify=classify)
+    assert np.isfinite(out["patch_tokens"]).all()
+    m = restate.RefModel(p)
+    r = restate.forward(m, imgs[1], classify=classify)
+    print(f"[parity] {name} outliers: |ref| mean {float(np.abs(r['patch_tokens']).mean()):.3f} max {float(np.abs(r['patch_tokens']).max()):.2f}")
+    _report(f"{name} outliers vs restatement", out["patch_tokens"][1], r["patch_tokens"])
+    assert nmse(out["patch_tokens"][1], r["patch_tokens"]) < NMSE_F16
+    assert nmse(out["cls"][1], r["cls"]) < NMSE_F16
+    if classify:
+        assert int(out["probs"][1].argmax()) == int(r["probs"].argmax())
+        assert nmse(out["logits"][1], r["logits"]) < NMSE_F16
+    if refmod.available():
+        R = refmod.Reference(p, classify=classify, H=518, W=518)
+        o = R.forward(imgs[0])
+        R.close()
+        if not classify:               # (tokens of the classify graph are recycled by ggml's allocator: see the ViT-L test)
+            inside = _report(f"{name} outliers vs reference", out["patch_tokens"][0], o["patch_tokens"])
+            assert nmse(out["patch_tokens"][0], o["patch_tokens"]) < NMSE_F16
+            assert inside > 0.99
+        if classify:
+            assert int(out["probs"][0].argmax()) == int(o["probs"].argmax())
+            assert nmse(out["logits"][0], o["logits"]) < NMSE_F16
