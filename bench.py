@@ -427,6 +427,41 @@ def main():
                           "value": B * world * n_f / (f_ms / 1e3), "unit": "images/s", "ms_per_step": f_ms / n_f, "steps": n_f,
                           "collective": "ncclAllGather of [B, D] fp32 cls embeddings (torch.distributed, NVLink)",
                           "gathered_bytes_per_rank": int(B * world * fw.D * 4), "collective_us_alone": coll_us}
+        # the engine's own exchange: the final LayerNorm of every rank stores its cls rows straight into every rank's gather
+        # buffer (peer memory opened through CUDA IPC handles) — no separate collective kernel at all
+        try:
+            import ctypes
+            gbuf, handle = fw.eng.gather_init(rank, world, d.GATHER_CLS, B, H, W)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            for r in range(world):
+                if r != rank:
+                    fw.eng.gather_set_peer(r, ipc_handle=handles[r])
+            barrier()
+
+            def step_fused():
+                fw.eng.forward_gather_device(fw.dev_in.data_ptr(), d.LAYOUT_BGR_HWC, B, H, W, stream=fw.stream.cuda_stream)
+
+            saved, fw.step_device = fw.step_device, step_fused
+            g_ms, _ = fw.time_device(n_f, 3, barrier)
+            fw.step_device = saved
+            g_ms = max_over_ranks([g_ms])[0]
+            # correctness of the exchange: rank 0's gather buffer == NCCL all-gather of every rank's cls output
+            fw.step_device()
+            dist.all_gather_into_tensor(g_out, fw.dev_cls)
+            torch.cuda.synchronize()
+            barrier()
+            mine = torch.empty(B * world, fw.D, device="cuda")
+            ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(mine.data_ptr()), ctypes.c_void_p(gbuf), B * world * fw.D * 4, 3)
+            same = bool(torch.equal(mine, g_out))
+            flags = torch.tensor([1.0 if same else 0.0], device="cuda")
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            scale_features["fused_peer_store"] = {"value": B * world * n_f / (g_ms / 1e3), "unit": "images/s", "ms_per_step": g_ms / n_f,
+                                                  "api": "dino_b200_gather_init / _set_peer (CUDA IPC) / _forward_gather_device",
+                                                  "kernel": "layernorm_gather_kernel: final LayerNorm + stores to every rank's buffer",
+                                                  "equals_nccl_all_gather_on_every_rank": bool(flags.item() == 1.0)}
+        except Exception as ex:
+            scale_features["fused_peer_store"] = {"error": str(ex)[:300]}
         if fw is not wl:
             fw.close()
 

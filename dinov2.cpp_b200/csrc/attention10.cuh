@@ -82,6 +82,10 @@ struct Attn10Params {
     int num_items;     // batch * n_heads * n_qblk
     __half *out;       // (unused by the kernel: the output is written through tmOut)
     float scale_log2;  // log2(e) / sqrt(64)
+    // -fa compatibility (reference dinov2.cpp:499-525): the flash path zero-pads Q, K, V to a multiple of 32 tokens and calls
+    // ggml_flash_attn_ext WITHOUT a mask, so every query also attends to n_phantom all-zero keys (score 0, value 0): they add
+    // n_phantom * exp(0 - max) to the softmax denominator and nothing to the numerator.  0 = exact attention (default path).
+    int n_phantom;
     unsigned long long *trace;   // AT10_TRACE builds only
 };
 
@@ -413,8 +417,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 // are rescaled) — probabilities stay <= 256, exact in fp16
                 const float mx0 = attn_rowmax32(c0);
                 if (j == 0) {
-                    m_used = mx0;                         // O_t is overwritten by the first P V of the item
-                    l_run = 0.f;
+                    m_used = p.n_phantom > 0 ? fmaxf(mx0, 0.f) : mx0;   // O_t is overwritten by the first P V of the item
+                    l_run = 0.f;                                        // (phantom keys have score 0: the reference covers them)
                 } else {
                     const bool grow = mx0 > m_used + thr;
                     if (__any_sync(0xffffffffu, grow)) {  // rare: O_t must be quiescent, i.e. P(j-1) V(j-1) complete
@@ -482,6 +486,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 AT10_SEV(17);
             }
             pending = true;
+            if (p.n_phantom > 0) l_run += static_cast<float>(p.n_phantom) * ex2_approx(-m_used * c);   // the zero keys of the -fa path
             pend_l = l_run;
             pend_c0 = it.head * 64;
             pend_c1 = it.qb * 256 + t * 128;

@@ -353,6 +353,7 @@ static unsigned long long *attention_trace_buffer(cudaStream_t st) {
 }
 
 template <typename Params> static Params attention_params(__half *out, int B, int n_tok, int D) {
+    // (n_phantom, where a kernel has it, is value-initialised to 0 = exact attention)
     Params ap{};
     ap.n_tok = n_tok;
     ap.hidden = D;
@@ -365,10 +366,11 @@ template <typename Params> static Params attention_params(__half *out, int B, in
     return ap;
 }
 
-static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, int num_sms, cudaStream_t st) {
+static void launch_attention(const CUtensorMap &tmQKV, __half *out, int B, int n_tok, int D, int num_sms, cudaStream_t st, bool fa_compat = false) {
     const int variant = attention_variant();
     if (variant == 10) {
         Attn10Params ap = attention_params<Attn10Params>(out, B, n_tok, D);
+        ap.n_phantom = fa_compat ? (32 - n_tok % 32) % 32 : 0;        // GGML_PAD(tokens, 32) - tokens (dinov2.cpp:499-500)
 #if defined(AT10_TRACE) || defined(AT10_PROF)
         ap.trace = attention_trace_buffer(st);
 #endif
@@ -934,7 +936,7 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
             prof.end();
         }
         prof.begin(1);
-        launch_attention(tm_qkv, e->AO, B, ntok, D, g_num_sms, st);
+        launch_attention(tm_qkv, e->AO, B, ntok, D, g_num_sms, st, (flags & DINO_B200_FLASH_ATTN_COMPAT) != 0);
         prof.end();
         {
             GemmParams gp{};
@@ -1836,7 +1838,7 @@ extern "C" dino_b200_status dino_b200_submit_u8(dino_b200_engine *e, const uint8
     DINO_CUDA(cudaEventRecord(e->ev_up[slot], e->copy_stream));
     DINO_CUDA(cudaStreamWaitEvent(st, e->ev_up[slot], 0));
     dino::preprocess_launch(e, e->d_u8s[slot], e->d_in[slot], B, H, W, classify, st);
-    dino::forward_device(e, e->d_in[slot], DINO_B200_LAYOUT_BGR_HWC, B, OH, OW, flags & DINO_B200_CLASSIFY, n_cls ? r_cls : nullptr,
+    dino::forward_device(e, e->d_in[slot], DINO_B200_LAYOUT_BGR_HWC, B, OH, OW, flags & (DINO_B200_CLASSIFY | DINO_B200_FLASH_ATTN_COMPAT), n_cls ? r_cls : nullptr,
                          n_patch ? r_patch : nullptr, n_log ? r_log : nullptr, n_prob ? r_prob : nullptr, st);
     if (pca_rgb) dino::pca_device(e, r_patch, B, static_cast<int>(np), e->r_rgb[slot], nullptr, st);
     DINO_CUDA(cudaEventRecord(e->ev_fwd[slot], st));
@@ -1953,7 +1955,7 @@ extern "C" dino_b200_status dino_b200_forward_gather_device(dino_b200_engine *e,
         throw dino::StatusError(DINO_B200_ERR_INVALID, "forward_gather: batch / image size differ from dino_b200_gather_init");
     DINO_CUDA(cudaSetDevice(e->device));
     dino::ensure_arena(e, B > 0 ? B : 1, H, W);
-    dino::forward_device(e, images, layout, B, H, W, (flags & DINO_B200_CLASSIFY) | dino::kFlagGather, cls, patch, logits, probs,
+    dino::forward_device(e, images, layout, B, H, W, (flags & (DINO_B200_CLASSIFY | DINO_B200_FLASH_ATTN_COMPAT)) | dino::kFlagGather, cls, patch, logits, probs,
                          stream ? static_cast<cudaStream_t>(stream) : e->stream);
     return DINO_B200_OK;
     DINO_API_END(e)
@@ -2044,7 +2046,7 @@ extern "C" dino_b200_status dino_b200_group_forward(dino_b200_group *g, const fl
         }
         cudaStream_t st = e->stream;
         DINO_CUDA(cudaMemcpyAsync(e->d_img, images + b0 * img_elems, nb * img_elems * sizeof(float), cudaMemcpyHostToDevice, st));
-        dino::forward_device(e, e->d_img, layout, nb, H, W, flags & DINO_B200_CLASSIFY, cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
+        dino::forward_device(e, e->d_img, layout, nb, H, W, flags & (DINO_B200_CLASSIFY | DINO_B200_FLASH_ATTN_COMPAT), cls ? e->o_cls : nullptr, patch ? e->o_patch : nullptr,
                              (classify && logits) ? e->logits : nullptr, (classify && probs) ? e->probs : nullptr, st);
         if (cls) DINO_CUDA(cudaMemcpyAsync(cls + static_cast<size_t>(b0) * D, e->o_cls, static_cast<size_t>(nb) * D * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (patch) DINO_CUDA(cudaMemcpyAsync(patch + static_cast<size_t>(b0) * np * D, e->o_patch, static_cast<size_t>(nb) * np * D * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdinov2_b200.so")
 LAYOUT_RGB_PLANAR = 0
 LAYOUT_BGR_HWC = 1
 FLAG_CLASSIFY = 1
+FLAG_FLASH_ATTN_COMPAT = 2     # -fa: the reference flash path's unmasked zero-padding keys (dinov2.cpp:499-525)
 
 EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_SWIGLU_F16, EPI_PATCH_F32 = range(5)
 
@@ -205,8 +206,8 @@ class Engine:
 
     # -- the hot path ------------------------------------------------------
     def forward(self, images: np.ndarray, classify: bool = False, layout: int = LAYOUT_BGR_HWC,
-                want_patch: bool = True, want_cls: bool = True, out: Optional[Dict[str, np.ndarray]] = None
-                ) -> Dict[str, np.ndarray]:
+                want_patch: bool = True, want_cls: bool = True, out: Optional[Dict[str, np.ndarray]] = None,
+                flash_attn_compat: bool = False) -> Dict[str, np.ndarray]:
         """images: float32 [B,H,W,3] (BGR_HWC, what dino_preprocess returns) or [B,3,H,W] (RGB_PLANAR).
         Host in, host out; synchronous.  `out` may carry preallocated (e.g. pinned) result arrays."""
         images = np.ascontiguousarray(images, dtype=np.float32)
@@ -228,7 +229,7 @@ class Engine:
             res.setdefault("logits", np.empty((B, Cn), np.float32))
             res.setdefault("probs", np.empty((B, Cn), np.float32))
         _check(load_library().dino_b200_forward(
-            self._h, images.ctypes.data, layout, B, H, W, FLAG_CLASSIFY if classify else 0,
+            self._h, images.ctypes.data, layout, B, H, W, (FLAG_CLASSIFY if classify else 0) | (FLAG_FLASH_ATTN_COMPAT if flash_attn_compat else 0),
             _host_ptr(res.get("cls")), _host_ptr(res.get("patch_tokens")),
             _host_ptr(res.get("logits")), _host_ptr(res.get("probs"))), self._h)
         return res

@@ -14,7 +14,8 @@
 //
 // Deliberate, documented deviations: dino_output::preds holds the top-k CLASS IDS (the reference stores
 // `(uint32_t)probability`, i.e. zeros, dinov2.cpp:975); `-o` sets image_out (the reference overwrites fname_inp,
-// dinov2.cpp:875-876); enable_flash_attn is accepted and ignored (the engine always computes exact attention).
+// dinov2.cpp:875-876); -fa (enable_flash_attn) selects DINO_B200_FLASH_ATTN_COMPAT: the phantom zero keys of the reference's
+// unmasked flash path are reproduced, the fp16 accumulator noise of ggml's CPU flash kernel is not.
 #include "dinov2.h"
 #include "ggml-backend.h"
 #include "dinov2_b200_batch.h"
@@ -258,9 +259,10 @@ std::unique_ptr<dino_output> dino_predict(const dino_model &model, const cv::Mat
     const int H = img.rows / ps * ps, W = img.cols / ps * ps;
     if (H != img.rows || W != img.cols) contiguous = cv::Mat(contiguous(cv::Rect(0, 0, W, H))).clone();
     auto output = std::make_unique<dino_output>();
+    const int fa = params.enable_flash_attn ? DINO_B200_FLASH_ATTN_COMPAT : 0;
     if (params.classify) {
         std::vector<float> probs(hp.num_classes);
-        if (dino_b200_forward(eng, (const float *) contiguous.data, DINO_B200_LAYOUT_BGR_HWC, 1, H, W, DINO_B200_CLASSIFY, nullptr,
+        if (dino_b200_forward(eng, (const float *) contiguous.data, DINO_B200_LAYOUT_BGR_HWC, 1, H, W, DINO_B200_CLASSIFY | fa, nullptr,
                               nullptr, nullptr, probs.data()) != DINO_B200_OK) {
             fprintf(stderr, "%s: dino_b200_forward() failed: %s\n", __func__, dino_b200_last_error(eng));
             return {};
@@ -279,7 +281,7 @@ std::unique_ptr<dino_output> dino_predict(const dino_model &model, const cv::Mat
     } else {
         const int np = (H / ps) * (W / ps);
         cv::Mat patch_tokens(np, (int) hp.hidden_size, CV_32F);
-        if (dino_b200_forward(eng, (const float *) contiguous.data, DINO_B200_LAYOUT_BGR_HWC, 1, H, W, 0, nullptr,
+        if (dino_b200_forward(eng, (const float *) contiguous.data, DINO_B200_LAYOUT_BGR_HWC, 1, H, W, fa, nullptr,
                               (float *) patch_tokens.data, nullptr, nullptr) != DINO_B200_OK) {
             fprintf(stderr, "%s: dino_b200_forward() failed: %s\n", __func__, dino_b200_last_error(eng));
             return {};
@@ -313,7 +315,8 @@ std::vector<std::unique_ptr<dino_output>> dino_predict_batch(const dino_model &m
     }
     const int np = (H / ps) * (W / ps), D = (int) hp.hidden_size, C = (int) hp.num_classes;
     std::vector<float> probs(params.classify ? (size_t) B * C : 0), patch(params.classify ? 0 : (size_t) B * np * D);
-    if (dino_b200_forward(eng, packed.data(), DINO_B200_LAYOUT_BGR_HWC, B, H, W, params.classify ? DINO_B200_CLASSIFY : 0, nullptr,
+    if (dino_b200_forward(eng, packed.data(), DINO_B200_LAYOUT_BGR_HWC, B, H, W,
+                          (params.classify ? DINO_B200_CLASSIFY : 0) | (params.enable_flash_attn ? DINO_B200_FLASH_ATTN_COMPAT : 0), nullptr,
                           params.classify ? nullptr : patch.data(), nullptr, params.classify ? probs.data() : nullptr) != DINO_B200_OK) {
         fprintf(stderr, "%s: dino_b200_forward() failed: %s\n", __func__, dino_b200_last_error(eng));
         return outs;
@@ -352,7 +355,7 @@ void print_usage(int, char **argv, const dino_params &params) {
     fprintf(stderr, "  -k N, --topk            top k classes to print (default: %d)\n", params.topk);
     fprintf(stderr, "  -t N, --threads         accepted for compatibility; the GPU engine ignores it (default: %d)\n", params.n_threads);
     fprintf(stderr, "  -c, --classify          classify the image instead of extracting backbone features (default: %d)\n", params.classify);
-    fprintf(stderr, "  -fa, --flash_attn       accepted for compatibility; attention is always exact (default: %d)\n", params.enable_flash_attn);
+    fprintf(stderr, "  -fa, --flash_attn       reproduce the reference flash path's unmasked zero-padding keys (default: %d)\n", params.enable_flash_attn);
     fprintf(stderr, "  -cid, --camera_id       camera id for realtime PCA feature streaming (default: %d)\n\n", params.camera_id);
 }
 

@@ -80,7 +80,15 @@ enum {
     DINO_B200_LAYOUT_BGR_HWC = 1     /* [B][H][W][3] float32 — the cv::Mat dino_preprocess returns (dinov2.cpp:135-156) */
 };
 /* forward flags */
-enum { DINO_B200_CLASSIFY = 1 }; /* dino_params::classify (dinov2.h:63): run forward_head (dinov2.cpp:792-821) */
+enum {
+    DINO_B200_CLASSIFY = 1,          /* dino_params::classify (dinov2.h:63): run forward_head (dinov2.cpp:792-821) */
+    /* dino_params::enable_flash_attn (-fa, dinov2.h:65): reproduce the SEMANTIC difference of the reference's flash path
+     * (dinov2.cpp:499-525): tokens are zero-padded to a multiple of 32 and ggml_flash_attn_ext runs without a mask, so each
+     * query also attends to the padding keys (score 0, value 0) — their weight is added to the softmax denominator.  Not
+     * reproduced: the fp16 running accumulator of ggml's CPU flash kernel (ops.cpp:6858-7075) and, for quantised checkpoints,
+     * the cast of K / V to the weight type.  Without this flag attention is exact (the reference's default path). */
+    DINO_B200_FLASH_ATTN_COMPAT = 2
+};
 
 /* Number of usable sm_100 devices (0 when none / no driver). */
 DINO_B200_API int dino_b200_device_count(void);
