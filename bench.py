@@ -48,14 +48,14 @@ def flops_per_image(cfg, n_tok: int) -> dict:
 
 
 def load_gemm_traffic():
-    """DRAM bytes per GEMM launch from the committed ncu --set full capture (profiles/r01_gemm_traffic.json), ViT-L b64 only."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    """DRAM bytes per GEMM launch from the committed ncu --set full capture (profiles/r02_gemm_traffic.json), ViT-L b64 only."""
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
         return {"bytes_per_launch": d["dram_bytes_per_launch_mean"],
                 "algorithmic_bytes_per_launch": sum(k["algorithmic_bytes"] for k in d["kernels"]) / len(d["kernels"]),
-                "source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the qkv / o-proj / fc1 / fc2 launches of one block)"}
+                "source": "profiles/r02_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the qkv / o-proj / fc1 / fc2 launches of one block)"}
     except Exception:
         return None
 

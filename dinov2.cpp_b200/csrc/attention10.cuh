@@ -86,6 +86,7 @@ struct Attn10Params {
     // ggml_flash_attn_ext WITHOUT a mask, so every query also attends to n_phantom all-zero keys (score 0, value 0): they add
     // n_phantom * exp(0 - max) to the softmax denominator and nothing to the numerator.  0 = exact attention (default path).
     int n_phantom;
+    int reverse;       // walk each CTA's work items from last to first (L2 reuse across consecutive kernels, see GemmParams::reverse)
     unsigned long long *trace;   // AT10_TRACE builds only
 };
 
@@ -113,6 +114,20 @@ struct Attn10Item {
                 ++img;
             }
         }
+    }
+    __device__ __forceinline__ void prev(int n_qblk, int n_heads) {
+        if (--qb < 0) {
+            qb = n_qblk - 1;
+            if (--head < 0) {
+                head = n_heads - 1;
+                --img;
+            }
+        }
+    }
+    // step in the walking direction of the kernel
+    __device__ __forceinline__ void step(int n_qblk, int n_heads, int reverse) {
+        if (reverse) prev(n_qblk, n_heads);
+        else next(n_qblk, n_heads);
     }
     __device__ __forceinline__ bool has_q1(int n_tok) const { return qb * 256 + 128 < n_tok; }
 };
@@ -180,6 +195,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_R = tmem_base;           // ring of tile t: columns 192 t + 64 slot
     const uint32_t tmem_O = tmem_base + 384;     // O_t at columns 384 + 64 t
+    griddep_wait();                              // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
+    griddep_launch_dependents();
 
     if (warp >= 8) {
         setmaxnreg_dec<80>();
@@ -188,8 +205,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             int s = 0;
             uint32_t ph = 0, li = 0;                       // K/V stage + phase; local item index (Q buffer = li & 1)
             Attn10Item it;
-            it.init(item_lo, p.n_qblk, p.n_heads);
-            for (int item = item_lo; item < item_hi; ++item, ++li, it.next(p.n_qblk, p.n_heads)) {
+            it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
+            for (int item = item_lo; item < item_hi; ++item, ++li, it.step(p.n_qblk, p.n_heads, p.reverse)) {
                 const int row_base = it.img * p.n_tok, q_base = it.qb * 256;
                 const bool has_q1 = it.has_q1(p.n_tok);
                 const uint32_t qb = li & 1;
@@ -259,7 +276,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         slot_s = slot_s == 2 ? 0u : slot_s + 1;                                                                        \
     } while (0)
             Attn10Item it;
-            it.init(item_lo, p.n_qblk, p.n_heads);
+            it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
             bool act = T == 0 || it.has_q1(p.n_tok);       // this warp's query tile exists in the current item
             // the very first S of this CTA
             mbar_wait(&q_full[0], 0);
@@ -270,7 +287,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             __syncwarp();
             for (int item = item_lo; item < item_hi; ++item, ++li) {
                 const bool has_next = item + 1 < item_hi;
-                it.next(p.n_qblk, p.n_heads);
+                it.step(p.n_qblk, p.n_heads, p.reverse);
                 const bool act_next = has_next && (T == 0 || it.has_q1(p.n_tok));
                 const uint64_t q_cur = q_desc_base + static_cast<uint64_t>((li & 1) * ((2 * AT10_TILE) >> 4));
                 const uint64_t q_nxt = q_desc_base + static_cast<uint64_t>(((li + 1) & 1) * ((2 * AT10_TILE) >> 4));
@@ -390,8 +407,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         }
 #endif
         Attn10Item it;
-        it.init(item_lo, p.n_qblk, p.n_heads);
-        for (int item = item_lo; item < item_hi; ++item, it.next(p.n_qblk, p.n_heads)) {
+        it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
+        for (int item = item_lo; item < item_hi; ++item, it.step(p.n_qblk, p.n_heads, p.reverse)) {
             if (t == 1 && !it.has_q1(p.n_tok)) continue;
             float m_used = -INFINITY;
             float l_run = 0.f;                            // softmax denominator relative to m_used

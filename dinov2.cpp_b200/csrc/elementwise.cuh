@@ -19,6 +19,8 @@ namespace dino {
 // every patch row are written by the threads of the patch's first pixel row.
 __global__ void im2col_patch14_kernel(const float *__restrict__ img, __half *__restrict__ A, int B, int H, int W, int ps,
                                       int gh, int gw, int kpad, int layout) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int HH = gh * ps, WW = gw * ps;                      // the part of the image covered by patches
     const long long total = static_cast<long long>(B) * HH * WW;
     const int kreal = 3 * ps * ps;
@@ -55,6 +57,8 @@ __global__ void im2col_patch14_kernel(const float *__restrict__ img, __half *__r
 // (reference dinov2.cpp:669-685).  grid = B, block covers D.
 __global__ void prefix_tokens_kernel(float *__restrict__ X, const float *__restrict__ cls, const float *__restrict__ pos,
                                      const float *__restrict__ reg, int ntok, int D, int R) {
+    griddep_wait();
+    griddep_launch_dependents();
     float *xb = X + static_cast<size_t>(blockIdx.x) * ntok * D;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         xb[d] = cls[d] + pos[d];
@@ -67,11 +71,14 @@ __global__ void prefix_tokens_kernel(float *__restrict__ X, const float *__restr
 template <bool OUT_HALF, int NV4 = LN_MAX_V4>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
-                 void *__restrict__ out, int rows, int D, float eps) {
+                 void *__restrict__ out, int rows, int D, float eps, int reverse) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const size_t off = static_cast<size_t>(warp) * D;
+    // reverse: the first blocks to be scheduled take the LAST rows (what the producer kernel wrote last is still in L2)
+    const size_t off = static_cast<size_t>(reverse ? rows - 1 - warp : warp) * D;
     void *orow = OUT_HALF ? static_cast<void *>(reinterpret_cast<__half *>(out) + off) : static_cast<void *>(reinterpret_cast<float *>(out) + off);
     layernorm_row<OUT_HALF, false, NV4>(X + off, gamma, beta, orow, D, eps, lane);
 }
@@ -85,6 +92,8 @@ template <int NV4 = LN_MAX_V4>
 __global__ void __launch_bounds__(256)
 layernorm_gather_kernel(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta, GatherDst dst,
                         int n_images, int ntok, int tok0, int rows_per_image, size_t slot_row0, int D, float eps) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_images * rows_per_image) return;
@@ -99,6 +108,8 @@ layernorm_gather_kernel(const float *__restrict__ X, const float *__restrict__ g
 // (img_size/patch)^2 and the sum includes register tokens (dinov2.cpp:770-776, 800-803); ggml_sum_rows
 // accumulates in double.  feat[b] = [cls ; pooled]  ([B, 2D] fp32).
 __global__ void pool_tokens_kernel(const float *__restrict__ Y, float *__restrict__ feat, int ntok, int D, float inv_div) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int b = blockIdx.y;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
@@ -112,6 +123,8 @@ __global__ void pool_tokens_kernel(const float *__restrict__ Y, float *__restric
 // logits[b][c] = sum_k fp16(feat[b][k]) * W[c][k] + bias[c]  (fp16 x fp16 -> f32, one warp per (b, c))
 __global__ void classifier_kernel(const float *__restrict__ feat, const __half *__restrict__ Wc, const float *__restrict__ bias,
                                   float *__restrict__ logits, int B, int K, int C) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= B * C) return;
@@ -131,6 +144,8 @@ __global__ void classifier_kernel(const float *__restrict__ feat, const __half *
 
 // probs = softmax(logits) per image (reference ggml_soft_max, ops.cpp:4641-4737). grid = B, block = 256.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ logits, float *__restrict__ probs, int C) {
+    griddep_wait();
+    griddep_launch_dependents();
     __shared__ float red[8];
     __shared__ float bcast;
     const float *x = logits + static_cast<size_t>(blockIdx.x) * C;

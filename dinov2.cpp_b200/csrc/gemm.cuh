@@ -53,6 +53,9 @@ struct GemmParams {
     int *ln_count;          // one counter per 128-row block, zero on entry and zero again on exit
     unsigned long long a_hint;   // L2 eviction-priority hints of the A (activation) / W (weight) loads; 0 = default (normal / evict-last)
     unsigned long long b_hint;
+    // Walk the tiles from the LAST row block to the first.  Consecutive kernels of the forward pass alternate their direction
+    // (engine.cu), so that the ~100 MB a kernel wrote last — still in the 126 MB L2 — are what its consumer reads first.
+    int reverse;
 };
 
 constexpr int GEMM_BM = 128;
@@ -157,6 +160,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    griddep_wait();                    // everything above overlapped the previous kernel's tail (programmatic dependent launch)
+    griddep_launch_dependents();
 
     if (warp == 10) {
         // ------------------------------------------------------------ TMA producer
@@ -170,7 +175,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint64_t a_hint = p.a_hint ? p.a_hint : kEvictNormal;
         const uint64_t b_hint = p.b_hint ? p.b_hint : kEvictLast;
         for (int t = tile0; t < num_tiles; t += tile_step) {
-            const int m_blk = t / num_n, n_blk = t % num_n;
+            const int tt = p.reverse ? num_tiles - 1 - t : t;
+            const int m_blk = tt / num_n, n_blk = tt % num_n;
             const int row_a = ((m_blk * MC + static_cast<int>(pair_idx)) * CG + static_cast<int>(cta_rank)) * GEMM_BM;   // this CTA's 128 A rows
             const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (BN / CG);          // this CTA's share of the weight rows
             for (int kb = 0; kb < num_k; ++kb) {
@@ -310,7 +316,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         };
         int it = 0;
         for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
-            const int m_blk = t / num_n, n_blk = t % num_n;
+            const int tt = p.reverse ? num_tiles - 1 - t : t;
+            const int m_blk = tt / num_n, n_blk = tt % num_n;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aph);

@@ -401,6 +401,15 @@ __device__ __forceinline__ f32x2 add2_f32_ordered(f32x2 a, f32x2 b) {
     return d;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels of the forward pass are launched with cudaLaunchAttributeProgrammaticStreamSerialization: kernel N+1 may be
+// scheduled while kernel N is still draining, runs its prologue (barrier init, TMEM allocation, tensor-map prefetch) and then
+// waits HERE until every grid it depends on has completed and flushed its memory.  Every global access of a kernel comes after
+// this wait.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the dependent grid start launching once every CTA of this grid has passed this point (or exited)
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);

@@ -37,7 +37,7 @@ def launches(path_csv, out_md, steps_hint):
     total = sum(tot.values())
     with open(out_md, "w") as f:
         f.write(f"# ncu launch list summary ({tag})\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n")
+        f.write("Command: `DINO_B200_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs` (tools/r02_profile.sh)\n")
         f.write(f"(ViT-L/14, 518x518, batch 64, classify; {len(seq)} launches captured = {steps_hint}). Per-launch times are serialised and\n"
                 "cold-cache under ncu: compare SHARES, not absolutes.\n\n")
         f.write("| kernel | launches | total ms | share | mean us |\n|---|---:|---:|---:|---:|\n")
@@ -71,7 +71,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 if os.path.exists(os.path.join(G, f"{tag}_launches_bench.csv")):
     launches(os.path.join(G, f"{tag}_launches_bench.csv"), os.path.join(P, f"{tag}_launches_bench.md"), "about 10 forward passes (warm-up, timed, end-to-end) + weight upload; capture capped by -c")
-for name, title in (("gemm", "GEMM kernels (gemm_f16_tcgen05)"), ("attn", "Attention kernel (attention_fwd_v8)")):
+for name, title in (("gemm", "GEMM kernels (gemm_f16_tcgen05): qkv, o-proj, fc1, fc2 of one block"), ("attn", "Attention kernel"),
+                    ("ln", "LayerNorm kernel (norm1 / norm2 of one block)")):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if os.path.exists(rep):
         raw_metrics(rep, os.path.join(P, f"{tag}_ncu_{name}.md"), title, WANT)
