@@ -91,6 +91,10 @@ __device__ __forceinline__ void attn_mask32(uint32_t (&v)[32], int valid) {
 #ifndef ATS_PIPE
 #define ATS_PIPE 1
 #endif
+// 1: the MUFU and row-sum instructions are volatile asm (fixed order among themselves at the NVVM level)
+#ifndef ATS_VOLATILE
+#define ATS_VOLATILE 1
+#endif
 template <int E0, int E1>
 __device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2]) {
 #if ATS_PACKED
@@ -125,15 +129,24 @@ __device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t
             } else {
                 float x0, x1;
                 unpack_f32x2(x, x0, x1);
+#if ATS_VOLATILE
                 p0 = ex2_approx_ordered(x0);
                 p1 = ex2_approx_ordered(x1);
+#else
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+#endif
             }
             q0[e - E0] = p0;
             q1[e - E0] = p1;
         }
         if (e - ATS_PIPE >= E0) {
             const int d = e - ATS_PIPE;
+#if ATS_VOLATILE
             acc = add2_f32_ordered(acc, pack_f32x2(q0[d - E0], q1[d - E0]));
+#else
+            acc = add2_f32(acc, pack_f32x2(q0[d - E0], q1[d - E0]));
+#endif
             pk[d] = cvt_f16x2(q0[d - E0], q1[d - E0]);
         }
     }
