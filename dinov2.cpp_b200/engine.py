@@ -14,7 +14,8 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdinov2_b200.so")
+# DINO_B200_LIB selects another build of the library (A/B variants from tools/build_variant.sh); default: the product build
+LIB_PATH = os.environ.get("DINO_B200_LIB") or os.path.join(_HERE, "lib", "libdinov2_b200.so")
 
 LAYOUT_RGB_PLANAR = 0
 LAYOUT_BGR_HWC = 1
