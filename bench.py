@@ -446,9 +446,12 @@ def main():
             g_ms, _ = fw.time_device(n_f, 3, barrier)
             fw.step_device = saved
             g_ms = max_over_ranks([g_ms])[0]
-            # correctness of the exchange: rank 0's gather buffer == NCCL all-gather of every rank's cls output
-            fw.step_device()
-            dist.all_gather_into_tensor(g_out, fw.dev_cls)
+            # correctness of the exchange: every rank's gather buffer == NCCL all-gather of every rank's cls output
+            # (same stream for the forward and the collective: the collective must see the finished dev_cls)
+            with torch.cuda.stream(fw.stream):
+                fw.step_device()
+                dist.all_gather_into_tensor(g_out, fw.dev_cls)
+                fw.stream.synchronize()
             torch.cuda.synchronize()
             barrier()
             mine = torch.empty(B * world, fw.D, device="cuda")

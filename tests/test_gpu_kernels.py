@@ -127,6 +127,24 @@ def test_attention(B, N, D):
     assert nmse_t(out, ref) < 5e-7
 
 
+@pytest.mark.parametrize("N", [1, 17, 32, 33, 96, 127, 128, 129, 160, 192, 224, 255, 256, 257, 288, 384, 385, 512, 640, 700])
+def test_attention_token_count_boundaries(N):
+    """Every boundary of the v10 tile logic: one tile / one query block (N <= 128, <= 256), a last key tile that ends exactly on a
+    32-key chunk (N % 128 in {32, 64, 96}: fully masked chunks are skipped, not exponentiated), ragged last chunks, a second query
+    tile that exists or not, items whose first tile is also their last (N <= 128)."""
+    B, D = 3, 128
+    g = torch.Generator(device="cuda").manual_seed(100 + N)
+    qkv = (torch.randn(B * N, 3 * D, device="cuda", generator=g) * 1.5).half()
+    buf = torch.full((B * N + 256, D), 7.0, device="cuda", dtype=torch.half)   # 256 guard rows after the output
+    buf[:B * N] = float("nan")
+    out = buf[:B * N]
+    E.kernel_attention(qkv.data_ptr(), out.data_ptr(), B, N, D)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert nmse_t(out, _attn_ref(qkv, B, N, D)) < 5e-7
+    assert bool((buf[B * N:] == 7.0).all())          # the TMA store clips the last query tile at the image's last token
+
+
 def _attn_ref(qkv, B, N, D):
     Hh = D // 64
     q, k, v = [t.view(B, N, Hh, 64).permute(0, 2, 1, 3) for t in qkv.float().split(D, dim=1)]
