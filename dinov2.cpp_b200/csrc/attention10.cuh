@@ -597,6 +597,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         if (warp == 0) { p.trace[6] = prof_acc[6]; p.trace[7] = prof_acc[7]; p.trace[8] = tot; p.trace[10] = prof_acc[10]; }
     }
 #endif
+    griddep_launch_dependents_late();
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {

@@ -209,6 +209,11 @@ static bool pdl_enabled() {
     static const bool v = [] { const char *e = getenv("DINO_B200_PDL"); return !(e && e[0] == '0'); }();
     return v;
 }
+// largest workload (token rows) that is launched with programmatic dependent launch; DINO_B200_PDL_ROWS overrides (A/B runs)
+static int pdl_max_rows() {
+    static const int v = [] { const char *e = getenv("DINO_B200_PDL_ROWS"); return e ? atoi(e) : 12288; }();
+    return v;
+}
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
     cudaLaunchConfig_t cfg{};
@@ -905,7 +910,7 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
     struct PdlScope {
         explicit PdlScope(bool on) { t_pdl = on; }
         ~PdlScope() { t_pdl = false; }
-    } pdl_scope(pdl_enabled() && !e->profiling && M <= 12288);
+    } pdl_scope(pdl_enabled() && !e->profiling && M <= pdl_max_rows());
     // Consecutive kernels walk their row blocks in opposite directions: what a kernel wrote last (up to ~100 MB still in
     // the 126 MB L2) is what its consumer reads first.  DINO_B200_ZIGZAG=0 switches the alternation off (A/B measurements).
     static const bool zigzag = [] { const char *v = getenv("DINO_B200_ZIGZAG"); return !(v && v[0] == '0'); }();

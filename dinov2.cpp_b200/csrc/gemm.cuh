@@ -464,6 +464,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) bulk_wait<0>();       // staging smem must outlive the last TMA store; global writes complete
     }
 
+    griddep_launch_dependents_late();
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all();    // the peer may still read this CTA's shared memory / arrive on its barriers
     else __syncthreads();

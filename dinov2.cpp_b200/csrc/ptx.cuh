@@ -407,8 +407,21 @@ __device__ __forceinline__ f32x2 add2_f32_ordered(f32x2 a, f32x2 b) {
 // waits HERE until every grid it depends on has completed and flushed its memory.  Every global access of a kernel comes after
 // this wait.  Without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// lets the dependent grid start launching once every CTA of this grid has passed this point (or exited)
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// lets the dependent grid start launching once every CTA of this grid has passed this point (or exited).
+// DINO_PDL_LATE (A/B builds): trigger at the END of each kernel instead of right after its own wait.
+#ifndef DINO_PDL_LATE
+#define DINO_PDL_LATE 0
+#endif
+__device__ __forceinline__ void griddep_launch_dependents() {
+#if !DINO_PDL_LATE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void griddep_launch_dependents_late() {
+#if DINO_PDL_LATE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
