@@ -150,8 +150,8 @@ template <int EPI> static void configure_gemm_mc() {
 }
 #endif
 template <int BN, int EPI> static void configure_gemm() {
-    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 1>::kSmemBytes));
-    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 2>::kSmemBytes));
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 1, EPI == EPI_RESID_LN_F32>::kSmemBytes));
+    DINO_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, 2, EPI == EPI_RESID_LN_F32>::kSmemBytes));
 }
 // Per-device state: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and SM counts may
 // differ between devices, so both are tracked per ordinal (one process may hold engines on several GPUs).
@@ -170,8 +170,6 @@ static void configure_current_device_locked(DeviceState &d, int dev) {
     configure_gemm_mc<EPI_GELU_F16>();
     configure_gemm_mc<EPI_RESID_F32>();
     configure_gemm_mc<EPI_SWIGLU_F16>();
-    configure_gemm<256, EPI_RESID_LN_F32>();
-    configure_gemm<128, EPI_RESID_LN_F32>();
     DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
     DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM_BYTES));
     DINO_CUDA(cudaFuncSetAttribute(attention_fwd_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM_BYTES));
@@ -183,6 +181,8 @@ static void configure_current_device_locked(DeviceState &d, int dev) {
     configure_gemm<128, EPI_GELU_F16>();
     configure_gemm<256, EPI_RESID_F32>();
     configure_gemm<128, EPI_RESID_F32>();
+    configure_gemm<256, EPI_RESID_LN_F32>();
+    configure_gemm<128, EPI_RESID_LN_F32>();
     configure_gemm<256, EPI_SWIGLU_F16>();
     configure_gemm<256, EPI_PATCH_F32>();
     configure_gemm<128, EPI_PATCH_F32>();
@@ -212,6 +212,12 @@ static bool pdl_enabled() {
 // largest workload (token rows) that is launched with programmatic dependent launch; DINO_B200_PDL_ROWS overrides (A/B runs)
 static int pdl_max_rows() {
     static const int v = [] { const char *e = getenv("DINO_B200_PDL_ROWS"); return e ? atoi(e) : 12288; }();
+    return v;
+}
+// largest workload (token rows) whose LayerNorms run inside the residual GEMMs (EPI_RESID_LN_F32) when DINO_B200_FUSE_LN is
+// unset: 0 = never (at full batch the fused kernels cost what the two apart do)
+static int fuse_ln_max_rows() {
+    static const int v = [] { const char *e = getenv("DINO_B200_FUSE_LN_ROWS"); return e ? atoi(e) : 0; }();
     return v;
 }
 template <typename... KArgs, typename... Args>
@@ -291,8 +297,8 @@ static void launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
     const int grid = std::max(1, std::min(tiles, sms / (CG * MC))) * CG * MC;      // persistent: one cluster per CG * MC SMs
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN, CG>::kSmemBytes;
+    cfg.blockDim = dim3(dino::gemm_threads(EPI));
+    cfg.dynamicSmemBytes = GemmCfg<BN, CG, EPI == EPI_RESID_LN_F32>::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -342,10 +348,8 @@ static void launch_gemm(int epi, GemmPlan plan, const CUtensorMap &tmA, const CU
     DINO_GEMM_CASE(128, EPI_GELU_F16);
     DINO_GEMM_CASE(256, EPI_RESID_F32);
     DINO_GEMM_CASE(128, EPI_RESID_F32);
-#ifdef DINO_B200_EXPERIMENTAL
     DINO_GEMM_CASE(256, EPI_RESID_LN_F32);
     DINO_GEMM_CASE(128, EPI_RESID_LN_F32);
-#endif
     DINO_GEMM_CASE(256, EPI_SWIGLU_F16);
     DINO_GEMM_CASE(256, EPI_PATCH_F32);
     DINO_GEMM_CASE(128, EPI_PATCH_F32);
@@ -838,7 +842,7 @@ static void ensure_arena(dino_b200_engine *e, int B, int H, int W) {
     arena_alloc(e->logits, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
     arena_alloc(e->probs, nb * std::max<size_t>(e->hp.num_classes, 1), e->stream);
     arena_alloc(e->o_cls, nb * D, e->stream);
-    arena_alloc(e->ln_count, rows / GEMM_BM + 2, e->stream);   // zeroed here; every launch leaves them zero again
+    arena_alloc(e->ln_count, 2 * (rows / GEMM_BM + 2) + 4, e->stream);   // block counters, slice counters, ticket: zeroed here; every launch leaves them zero again
     DINO_CUDA(cudaStreamSynchronize(e->stream));
     e->cap_tok = ntok;
     e->cap_patch = npatch;
@@ -959,16 +963,14 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
     prof.end();
 
     // 2. encoder blocks
-    // DINO_B200_FUSE_LN=1 fuses norm2 into the o-proj GEMM's epilogue and the next block's norm1 into the fc2 GEMM's
-    // (EPI_RESID_LN_F32).  Correct (bit-identical to the stand-alone kernel, tests/test_gpu_kernels.py) but OFF by default:
-    // measured on B200 it is slower (o-proj + LN 857 us fused vs 186 + 99 us apart at ViT-L, batch 64): the 8 epilogue
-    // warps of a CTA normalise a 128-row block at ~17 GB/s (latency-bound L2 read-back), and because the CTA that
-    // finishes a row block LAST does the work, it keeps landing on the CTAs that are already behind.
-#ifdef DINO_B200_EXPERIMENTAL
-    static const bool fuse_ln = [] { const char *e = getenv("DINO_B200_FUSE_LN"); return e && e[0] == '1'; }();
-#else
-    constexpr bool fuse_ln = false;
-#endif
+    // With DINO_B200_FUSE_LN=1 norm2 runs inside the o-proj GEMM and the next block's norm1 inside the fc2 GEMM
+    // (EPI_RESID_LN_F32: LayerNorm worker warps normalise each row block out of L2 as soon as its last column tile has been
+    // added; bit-identical to the stand-alone kernel, tests/test_gpu_kernels.py).  Off by default: measured equal at full
+    // batch (the step is power-limited) and slower at batch 1 — DESIGN.md section 5.
+    static const int fuse_ln_env = [] { const char *e = getenv("DINO_B200_FUSE_LN"); return e ? atoi(e) : -1; }();   // -1 = by size
+    static const int ln_slice_env = [] { const char *e = getenv("DINO_B200_LN_SLICE"); return e ? atoi(e) : 0; }();
+    const bool fuse_ln = dino::gemm_ln_width_ok(D) && (fuse_ln_env < 0 ? M <= fuse_ln_max_rows() : fuse_ln_env != 0);
+    const int ln_slice = ln_slice_env > 0 ? ln_slice_env : (M <= fuse_ln_max_rows() ? 4 : 16);
     const size_t n_layers = e->layers.size();
     for (size_t li = 0; li < n_layers; ++li) {
         const Layer &ly = e->layers[li];
@@ -994,7 +996,7 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
             GemmParams gp{};
             gp.M = M; gp.N = D; gp.K = D; gp.bias = ly.proj.bias; gp.lscale = ly.ls1; gp.out = e->X; gp.ldo = D;
             gp.reverse = next_dir();
-            gp.ln_gamma = ly.ln2_g; gp.ln_beta = ly.ln2_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
+            gp.ln_gamma = ly.ln2_g; gp.ln_beta = ly.ln2_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count; gp.ln_slice = ln_slice;
             prof.begin(0);
             const int epi = fuse_ln ? EPI_RESID_LN_F32 : EPI_RESID_F32;
             const GemmPlan pl = plan_gemm(epi, gp.M, gp.N, g_num_sms);
@@ -1024,7 +1026,7 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
             const bool fuse_next = fuse_ln && li + 1 < n_layers;     // the next block's norm1; the last block feeds the final norm
             if (fuse_next) {
                 const Layer &nx = e->layers[li + 1];
-                gp.ln_gamma = nx.ln1_g; gp.ln_beta = nx.ln1_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count;
+                gp.ln_gamma = nx.ln1_g; gp.ln_beta = nx.ln1_b; gp.ln_out = e->Xn; gp.ln_eps = hp.eps; gp.ln_count = e->ln_count; gp.ln_slice = ln_slice;
             }
             prof.begin(0);
             const int epi = fuse_next ? EPI_RESID_LN_F32 : EPI_RESID_F32;
@@ -1677,16 +1679,9 @@ dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const vo
                                                 const float *lscale, float *X, const float *gamma, const float *beta, float eps,
                                                 void *ln_out, int *counters, void *stream) {
     DINO_API_BEGIN
-#ifndef DINO_B200_EXPERIMENTAL
-    (void) A; (void) lda; (void) W; (void) ldw; (void) M; (void) N; (void) K; (void) bias; (void) lscale; (void) X; (void) gamma;
-    (void) beta; (void) eps; (void) ln_out; (void) counters; (void) stream;
-    throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED,
-                            "kernel_gemm_resid_ln: the fused residual + LayerNorm epilogue measured slower than the two kernels apart "
-                            "and is only compiled with -DDINO_B200_EXPERIMENTAL");
-#else
     if (!A || !W || !X || !bias || !lscale || !gamma || !beta || !ln_out || !counters)
         throw dino::StatusError(DINO_B200_ERR_INVALID, "kernel_gemm_resid_ln: NULL argument");
-    if (N % 128 || N > 128 * dino::LN_MAX_V4) throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED, "kernel_gemm_resid_ln: N must be a multiple of 128, at most 1536");
+    if (!dino::gemm_ln_width_ok(N)) throw dino::StatusError(DINO_B200_ERR_UNSUPPORTED, "kernel_gemm_resid_ln: N must be 384, 768, 1024 or 1536");
     int dev = 0;
     DINO_CUDA(cudaGetDevice(&dev));
     if (!device_is_sm100(dev)) throw dino::StatusError(DINO_B200_ERR_NO_DEVICE, "current device is not sm_100");
@@ -1700,7 +1695,6 @@ dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const vo
     const CUtensorMap tmC = dino::make_tmap_out(dino::EPI_RESID_LN_F32, X, N, M, N);
     dino::launch_gemm(dino::EPI_RESID_LN_F32, pl, tmA, tmB, tmC, gp, static_cast<cudaStream_t>(stream));
     return DINO_B200_OK;
-#endif
     DINO_API_END(static_cast<dino_b200_engine *>(nullptr))
 }
 

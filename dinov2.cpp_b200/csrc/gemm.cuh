@@ -25,11 +25,14 @@
 //   EPI_PATCH_F32   X[b, 1+R+p] = acc + b + pos[1+p]              patch-embed GEMM + bias + pos-embed + token
 //                                                                 placement (dinov2.cpp:636-685)
 //   EPI_RESID_LN_F32  as RESID, plus the LayerNorm that follows the residual in the graph (norm2 after the attention
-//                   branch, the next block's norm1 after the MLP; dinov2.cpp:722-728, 694-700): every CTA counts the
-//                   column tiles it has added to each 128-row block of X; the CTA that adds the last one normalises those
-//                   rows (read back from L2, where the reduce-adds just left them) and writes the fp16 A operand of the
-//                   next GEMM.  Saves the stand-alone LayerNorm kernel's pass over X in HBM (2 x 359 MB per block at
-//                   ViT-L, batch 64) and its launch.
+//                   branch, the next block's norm1 after the MLP; dinov2.cpp:722-728, 694-700), done by the two warps that
+//                   are otherwise idle (8: TMEM allocator, 9): the epilogue warps count the column tiles added to each
+//                   128-row block of X; the worker warps of ALL CTAs draw 8-row slices from a global ticket, wait until
+//                   the slice's block is complete, normalise its rows (read back from L2, where the reduce-adds just left
+//                   them, four rows in flight per warp) and write the fp16 A operand of the next GEMM.  The GEMM pipeline
+//                   never waits for them.  Saves the stand-alone LayerNorm kernel's pass over X in HBM (359 MB per
+//                   LayerNorm at ViT-L, batch 64), its launch and its 86 us.  (Round 1's version let the epilogue warps of
+//                   whichever CTA finished a block do the rows, one at a time: 3x slower than the two kernels apart.)
 #pragma once
 #include "ptx.cuh"
 #include "ln_row.cuh"
@@ -48,9 +51,11 @@ struct GemmParams {
     int np, ntok, tok_off;  // (PATCH) patches / image, tokens / image, 1 + registers
     // (RESID_LN) LayerNorm of the finished rows of `out`: fp16 ln_out[M, N] = LN(out row) * ln_gamma + ln_beta
     const float *ln_gamma, *ln_beta;
+    int ln_slice;                       // rows per LayerNorm work item (a divisor of 128; 0 = GEMM_LN_SLICE)
     __half *ln_out;
     float ln_eps;
-    int *ln_count;          // one counter per 128-row block, zero on entry and zero again on exit
+    int *ln_count;          // column tiles added per 128-row block; ln_count[nblk .. 2 nblk) = slices normalised per block;
+                            // ln_count[2 nblk] = slice ticket, [2 nblk + 1] = workers finished.  All zero on entry and on exit.
     unsigned long long a_hint;   // L2 eviction-priority hints of the A (activation) / W (weight) loads; 0 = default (normal / evict-last)
     unsigned long long b_hint;
     // Walk the tiles from the LAST row block to the first.  Consecutive kernels of the forward pass alternate their direction
@@ -61,6 +66,13 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
+// EPI_RESID_LN_F32 runs 16 warps: the same 8 epilogue warps, the TMA and MMA warps, and SIX LayerNorm worker warps (8, 9, 12-15).
+// One worker warp retires a row in ~1.6 k cycles of dependent arithmetic and shuffles whatever the number of rows it keeps in
+// flight, so the worker count — not memory-level parallelism — sets the LayerNorm throughput; the residual epilogue needs
+// 126 registers, which fits the 128 a 512-thread CTA leaves per thread.
+constexpr int GEMM_THREADS_LN = 512;
+constexpr int GEMM_LN_WORKERS = 6;
+__host__ __device__ constexpr int gemm_threads(int epi) { return epi == EPI_RESID_LN_F32 ? GEMM_THREADS_LN : GEMM_THREADS; }
 constexpr int GEMM_EPI_WARPS = 8;
 // accumulator column blocks issued round-robin per k-block (1 = one MMA per k-step; 2 and 4 measured no faster)
 #ifndef GEMM_NSPLIT
@@ -71,14 +83,16 @@ constexpr int GEMM_EPI_WARPS = 8;
 // computes a 256 x BN tile: each CTA loads its 128 A rows and HALF of the BN weight rows, the pair's tensor cores read
 // both halves — per-CTA shared-memory fill and operand-read traffic drop by a third, which is what limits the 1-CTA
 // kernel (48 KB of TMA writes + 48 KB of operand reads per 512 MMA cycles against a 128 B/clk shared-memory port).
-template <int BN, int CG> struct GemmCfg {
+// LN (EPI_RESID_LN_F32): 12 KB of the operand ring become a shared-memory copy of the LayerNorm gamma / beta for the workers.
+template <int BN, int CG, bool LN = false> struct GemmCfg {
     static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;          // 16 KB
     static constexpr int kBBytes = (BN / CG) * GEMM_BK * 2;        // this CTA's share of the weight tile
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (192 * 1024) / kStageBytes;     // 4 (BN 256, CG 1) .. 8
+    static constexpr int kGbBytes = LN ? 2 * 1536 * 4 : 0;
+    static constexpr int kStages = (192 * 1024 - kGbBytes) / kStageBytes;     // 4 (BN 256, CG 1) .. 8
     static constexpr int kBarBytes = 256;
     static constexpr int kEpiBytes = GEMM_EPI_WARPS * 4096;   // one 32-row x 128-B staging tile per epilogue warp
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;   // +1024: manual alignment
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kGbBytes + 1024;   // +1024: manual alignment
     static constexpr int kTmemCols = 512;
 };
 
@@ -94,15 +108,121 @@ __device__ __forceinline__ float silu_f32(float x) {
     return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
 
+// LayerNorm worker of the residual GEMM (EPI_RESID_LN_F32), one warp.  Kept out of line and handed plain values: its row buffers
+// get their own register allocation instead of competing with the epilogue's inside one 168-register kernel body.
+// Slices of GEMM_LN_SLICE rows are drawn from a global ticket in the order the row blocks complete; a slice waits until all column tiles
+// of its 128-row block have been added (counter published by the epilogue warps, one tile late), then its rows are read back
+// from L2, R at a time, and normalised.  Nothing in the GEMM pipeline waits for these warps.
+// Widths: exactly 128 * NV4 columns (384, 768, 1024, 1536 = every DINOv2 hidden size; gemm_ln_width_ok).
+#ifndef GEMM_LN_SLICE
+#define GEMM_LN_SLICE 16
+#endif
+__host__ __device__ constexpr bool gemm_ln_width_ok(int N) { return N == 384 || N == 768 || N == 1024 || N == 1536; }
+
+template <int NV4, int R>
+__device__ __noinline__ void gemm_ln_worker(const float *X, size_t ldx, const float4 *gs, __half *ln_out,
+                                            int *ln_count, int M, float eps, int num_n, int reverse, int slice_rows, int lane) {
+    const int kSlicesPerBlk = GEMM_BM / slice_rows;
+    constexpr int N = NV4 * 128;
+    const int n_blk128 = (M + GEMM_BM - 1) / GEMM_BM;
+    const int n_slices = (M + slice_rows - 1) / slice_rows;
+    int *ln_done = ln_count + n_blk128;
+    int *ticket = ln_count + 2 * n_blk128;
+    int *finished = ticket + 1;
+#ifdef GEMM_LN_PROF
+    long long t_tick = 0, t_wait = 0, t_rows = 0, t_done = 0, n_sl = 0;
+    long long tq = clock64();
+#define LNP(ACC) do { const long long now__ = clock64(); ACC += now__ - tq; tq = now__; } while (0)
+#else
+#define LNP(ACC) do {} while (0)
+#endif
+    // The ticket of the NEXT slice and the completion count of the PREVIOUS one are in flight while a slice's rows are
+    // processed: their L2 round trips (1-2 k cycles each under load) stay off the worker's critical path.
+    int w_next = 0, done_prev = 0, blk_prev = -1;
+    if (lane == 0) w_next = atomicAdd(ticket, 1);
+    auto retire = [&]() {                                        // the last slice of a block puts the block's counters back to zero
+        if (lane == 0 && blk_prev >= 0) {
+            const int slices_in_blk = min(kSlicesPerBlk, n_slices - blk_prev * kSlicesPerBlk);
+            if (done_prev == slices_in_blk - 1) {
+                ln_count[blk_prev] = 0;
+                ln_done[blk_prev] = 0;
+            }
+        }
+    };
+    while (true) {
+        const int w = __shfl_sync(0xffffffffu, w_next, 0);
+        LNP(t_tick);
+        if (w >= n_slices) break;
+        if (lane == 0) w_next = atomicAdd(ticket, 1);
+        const int sl = reverse ? n_slices - 1 - w : w;
+        const int blk = sl / kSlicesPerBlk;
+        if (lane == 0) {
+#ifdef GEMM_LN_SC_FENCE
+            const volatile int *cnt = ln_count + blk;
+            while (*cnt < num_n) __nanosleep(64);
+            __threadfence();
+#else
+            while (ld_acquire_gpu(ln_count + blk) < num_n) __nanosleep(64);   // acquire: the rows added before the counter reached num_n
+#endif
+        }
+        __syncwarp();
+        LNP(t_wait);
+        const int r0 = sl * slice_rows, nr = min(slice_rows, M - r0);
+        const float *xs = X + static_cast<size_t>(r0) * ldx;
+        __half *os = ln_out + static_cast<size_t>(r0) * N;
+#pragma unroll 1
+        for (int r = 0; r < nr; r += R)
+            layernorm_rows_l2<NV4, R>(xs + static_cast<size_t>(r) * ldx, ldx, gs, os + static_cast<size_t>(r) * N, eps, lane, nr - r);
+        LNP(t_rows);
+        retire();
+        if (lane == 0) done_prev = atomicAdd(ln_done + blk, 1);
+        blk_prev = blk;
+#ifdef GEMM_LN_PROF
+        LNP(t_done);
+        ++n_sl;
+#endif
+    }
+    retire();
+#ifdef GEMM_LN_PROF
+    if (blockIdx.x == 0 && (threadIdx.x >> 5) == 8 && lane == 0) {
+        int *o = ticket + 2;
+        o[0] = static_cast<int>(t_tick); o[1] = static_cast<int>(t_wait); o[2] = static_cast<int>(t_rows); o[3] = static_cast<int>(t_done); o[4] = static_cast<int>(n_sl);
+    }
+#endif
+    // ... and the last worker of the grid the ticket
+    if (lane == 0) {
+        if (atomicAdd(finished, 1) == static_cast<int>(gridDim.x) * GEMM_LN_WORKERS - 1) {
+            *ticket = 0;
+            *finished = 0;
+            __threadfence();
+        }
+    }
+}
+
+#ifndef GEMM_LN_R8
+#define GEMM_LN_R8 3     // rows in flight per worker warp at width 1024 (96 data registers of the 128 a 512-thread CTA allows)
+#endif
+__device__ __forceinline__ void gemm_ln_worker_dispatch(const GemmParams &p, const float4 *gs, int num_n, int lane) {
+    const float *X = reinterpret_cast<const float *>(p.out);
+    const int slice_rows = p.ln_slice > 0 ? p.ln_slice : GEMM_LN_SLICE;
+    switch (p.N) {
+    case 384:  gemm_ln_worker<3, 8>(X, p.ldo, gs, p.ln_out, p.ln_count, p.M, p.ln_eps, num_n, p.reverse, slice_rows, lane); break;
+    case 768:  gemm_ln_worker<6, 4>(X, p.ldo, gs, p.ln_out, p.ln_count, p.M, p.ln_eps, num_n, p.reverse, slice_rows, lane); break;
+    case 1024: gemm_ln_worker<8, GEMM_LN_R8>(X, p.ldo, gs, p.ln_out, p.ln_count, p.M, p.ln_eps, num_n, p.reverse, slice_rows, lane); break;
+    case 1536: gemm_ln_worker<12, 2>(X, p.ldo, gs, p.ln_out, p.ln_count, p.M, p.ln_eps, num_n, p.reverse, slice_rows, lane); break;
+    default: break;                                              // the host refuses other widths (gemm_ln_width_ok)
+    }
+}
+
 // MC = 2 (only with CG = 2): clusters of FOUR CTAs = two CTA pairs that work on the same weight tile and on vertically adjacent
 // 256-row blocks of A.  Every CTA fetches a quarter of the 256 x 64 weight tile per k-block and TMA-multicasts it to the
 // CTA that holds the same half in the other pair, so the weight bytes cross the L2 -> SM fabric once per cluster instead of
 // once per pair (-25 % operand traffic per FLOP).  A stage is refilled only after BOTH pairs' MMAs have released it.
 template <int BN, int EPI, int CG, int MC = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, EPI == EPI_RESID_LN_F32>;
     static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
     static_assert(MC == 1 || (MC == 2 && CG == 2), "weight multicast couples two CTA pairs");
     static_assert(EPI != EPI_SWIGLU_F16 || BN == 256, "SwiGLU tiles pair 128 gate + 128 up columns");
@@ -118,7 +238,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    uint32_t *ln_flag = tmem_ptr + 1;                    // (RESID_LN) broadcast: this CTA completed a row block
+    float4 *smem_gb = reinterpret_cast<float4 *>(smem_epi + Cfg::kEpiBytes + Cfg::kBarBytes);   // gamma[N] | beta[N] (EPI_RESID_LN_F32)
     constexpr bool kResid = EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN_F32;
 
     const int warp = threadIdx.x >> 5;
@@ -154,6 +274,13 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 8) {
         if constexpr (CG == 2) tmem_alloc_2sm(tmem_ptr, Cfg::kTmemCols);
         else tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    }
+    if constexpr (EPI == EPI_RESID_LN_F32) {                  // weights, not a product of the previous kernel: no dependency wait
+        const int nv = p.N >> 2;
+        for (int i = threadIdx.x; i < nv; i += gemm_threads(EPI)) {
+            smem_gb[i] = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma) + i);
+            smem_gb[nv + i] = __ldg(reinterpret_cast<const float4 *>(p.ln_beta) + i);
+        }
     }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all();                // barrier inits visible to the peer before any remote arrive
@@ -259,6 +386,9 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
+    } else if (EPI == EPI_RESID_LN_F32 && (warp == 8 || warp == 9 || warp >= 12)) {
+        // ------------------------------------------------------------ LayerNorm workers (the two warps with no other job)
+        gemm_ln_worker_dispatch(p, smem_gb, num_n, lane);
     } else if (warp < 8) {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -291,28 +421,16 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 else bulk_wait<kResidSteps>();
             }
             __syncwarp();
-            named_bar_sync(1, GEMM_EPI_WARPS * 32);
-            if (threadIdx.x == 0) {
+            named_bar_sync(1, GEMM_EPI_WARPS * 32);               // every epilogue warp's reduce-adds of that tile have been performed
+            if (threadIdx.x == 0 && blk * GEMM_BM < p.M) {        // (the second CTA of the last pair may hold no rows at all)
                 fence_proxy_async_all();
+#ifdef GEMM_LN_SC_FENCE
                 __threadfence();
-                const int done = atomicAdd(p.ln_count + blk, 1) + 1;
-                const bool last = done == num_n;
-                if (last) p.ln_count[blk] = 0;                     // ready for the next launch
-                __threadfence();
-                *ln_flag = last ? 1u : 0u;
+                atomicAdd(p.ln_count + blk, 1);
+#else
+                red_add_release_gpu(p.ln_count + blk, 1);           // one more column tile of this 128-row block is in X
+#endif
             }
-            named_bar_sync(1, GEMM_EPI_WARPS * 32);
-            if (*ln_flag) {
-                const int r0 = blk * GEMM_BM + warp * (GEMM_BM / GEMM_EPI_WARPS);
-#pragma unroll 1
-                for (int rr = 0; rr < GEMM_BM / GEMM_EPI_WARPS; ++rr) {
-                    const int row = r0 + rr;
-                    if (row >= p.M) break;
-                    layernorm_row<true, true>(reinterpret_cast<const float *>(p.out) + static_cast<size_t>(row) * p.ldo, p.ln_gamma,
-                                              p.ln_beta, p.ln_out + static_cast<size_t>(row) * p.N, p.N, p.ln_eps, lane);
-                }
-            }
-            // (the flag is rewritten only after the next publication's first named barrier, which every warp reaches after this read)
         };
         int it = 0;
         for (int t = tile0; t < num_tiles; t += tile_step, ++it) {

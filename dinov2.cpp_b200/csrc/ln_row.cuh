@@ -60,6 +60,58 @@ __device__ __forceinline__ void layernorm_row(const float *__restrict__ xrow, co
     }
 }
 
+// R rows at once, same arithmetic per row as layernorm_row<true, true> (bit-identical fp16 output): the loads of all R rows are
+// issued before any reduction, so a warp that reads its rows from L2 (latency 1-2 us under load) keeps R x D x 4 bytes in
+// flight.  The row width is EXACTLY 128 * NV4 and nothing is predicated per element: with `if (idx < nv)` around the loads ptxas
+// kept the row buffer in local memory and, worse, put a store behind every load — the in-order warp then waited out one L2
+// round trip per load (measured 16 k cycles per pair of rows).  Rows are `ld` elements apart (input) / D apart (output); rows
+// >= n_rows (warp-uniform) re-read the last valid row and store nothing.
+// Used by the LayerNorm worker warps of the residual GEMM (gemm.cuh, EPI_RESID_LN_F32).
+// gamma / beta come from shared memory (gs: gamma as float4[NV4 * 32], beta right behind it): the GEMM's shared-memory
+// carve-out leaves almost no L1, so per-row global reads of them were a second serial L2 round trip per row and doubled the
+// worker's L2 traffic (ncu: 718 MB of gamma / beta sectors per launch).
+template <int NV4, int R>
+__device__ __forceinline__ void layernorm_rows_l2(const float *__restrict__ x, size_t ld, const float4 *gs,
+                                                  __half *__restrict__ out, float eps, int lane, int n_rows) {
+    constexpr int D = NV4 * 128;
+    float4 v[R][NV4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x + static_cast<size_t>(min(r, n_rows - 1)) * ld) + lane;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) v[r][i] = __ldcg(x4 + 32 * i);
+    }
+    const float4 *g4 = gs + lane;
+    const float4 *b4 = gs + NV4 * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / static_cast<float>(D);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+            v[r][i].x -= mean; v[r][i].y -= mean; v[r][i].z -= mean; v[r][i].w -= mean;
+            sq += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = 1.0f / sqrtf(sq / static_cast<float>(D) + eps);
+        if (r < n_rows) {
+            uint2 *o2 = reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * D) + lane;
+#pragma unroll
+            for (int i = 0; i < NV4; ++i) {
+                const float4 g = g4[32 * i], b = b4[32 * i];
+                o2[32 * i] = make_uint2(pack_half2((v[r][i].x * rstd) * g.x + b.x, (v[r][i].y * rstd) * g.y + b.y),
+                                        pack_half2((v[r][i].z * rstd) * g.z + b.z, (v[r][i].w * rstd) * g.w + b.w));
+            }
+        }
+    }
+}
+
 // Destinations of the fused final-LayerNorm + all-gather kernel: the same row is stored into the gather buffer of every rank
 // (peer device memory over NVLink / NVSwitch, or this device for the rank's own copy).
 struct GatherDst {

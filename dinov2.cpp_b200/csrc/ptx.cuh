@@ -214,6 +214,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t &r) {
 }
 
 // warpgroup-wide register reallocation (all 4 warps of the warpgroup must execute it)
+// gpu-scope release / acquire on a flag word: what __threadfence() + atomicAdd / a volatile poll + __threadfence() express,
+// without the sequentially-consistent fence (MEMBAR.SC.GPU + L1 invalidate) that __threadfence() compiles to.
+__device__ __forceinline__ void red_add_release_gpu(int *addr, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int *addr) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 

@@ -259,9 +259,9 @@ DINO_B200_API dino_b200_status dino_b200_kernel_gemm(int epi, const void *A, int
                                                      const float *bias, const float *lscale, void *out, int ldo,
                                                      const float *pos, int np, int ntok, int tok_off, void *stream);
 /* The fused residual + LayerNorm GEMM (reference dinov2.cpp:546-551 + 708-714 + 722-728):
- * X[M,N](fp32) += lscale * (A x W^T + bias), then ln_out[M,N](fp16) = LayerNorm(X row; eps) * gamma + beta, written by
- * whichever CTA completes a 128-row block.  counters: ceil(M/128)+1 ints, zero on entry, zero again on exit.
- * N must be a multiple of 128 and at most 1536. */
+ * X[M,N](fp32) += lscale * (A x W^T + bias), then ln_out[M,N](fp16) = LayerNorm(X row; eps) * gamma + beta, written by the
+ * kernel's LayerNorm worker warps as soon as a 128-row block of X is complete (bit-identical to dino_b200_kernel_layernorm on
+ * the updated X).  counters: 2 * ceil(M/128) + 2 ints, zero on entry, zero again on exit.  N must be 384, 768, 1024 or 1536. */
 DINO_B200_API dino_b200_status dino_b200_kernel_gemm_resid_ln(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                                                               const float *bias, const float *lscale, float *X,
                                                               const float *gamma, const float *beta, float eps, void *ln_out,

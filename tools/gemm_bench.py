@@ -59,7 +59,7 @@ for name, epi, N, K in shapes:
         # the same GEMM with the following LayerNorm fused into its epilogue, and the stand-alone LayerNorm it replaces
         gam = torch.randn(N, device="cuda"); bet = torch.randn(N, device="cuda")
         ln = torch.empty(M, N, device="cuda", dtype=torch.half)
-        cnt = torch.zeros((M + 127) // 128 + 1, device="cuda", dtype=torch.int32)
+        cnt = torch.zeros(2 * ((M + 127) // 128) + 2, device="cuda", dtype=torch.int32)
         def run2():
             E.kernel_gemm_resid_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), ls.data_ptr(), out.data_ptr(),
                                    gam.data_ptr(), bet.data_ptr(), 1e-6, ln.data_ptr(), cnt.data_ptr())
