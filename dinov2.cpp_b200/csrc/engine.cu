@@ -1070,7 +1070,7 @@ static uint64_t forward_enqueue(dino_b200_engine *e, const float *images, int la
                                     cudaMemcpyDeviceToDevice, st));
     if (classify) {
         const int n_embd = hp.img_size / ps;
-        launch_k(pool_tokens_kernel, dim3((D + 127) / 128, B), dim3(128), 0, st, e->Y, e->feat, ntok, D, 1.0f / static_cast<float>(n_embd * n_embd));
+        launch_k(pool_tokens_kernel, dim3((D + 127) / 128, B), dim3(POOL_THREADS), 0, st, e->Y, e->feat, ntok, D, 1.0f / static_cast<float>(n_embd * n_embd));
         DINO_CUDA(cudaGetLastError());
         const int C = hp.num_classes;
         const long long warps = static_cast<long long>(B) * C;
