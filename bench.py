@@ -14,8 +14,9 @@ Printed JSON (rank 0, one line):
                 CUDA-event timed on the launching stream, max over ranks)
   e2e           same metric through the host-buffer C ABI call (dino_b200_forward): H2D of the batch from
                 pinned memory + D2H of the result inside the timed region
-  roofline      tensor-core roofline of the dominant kernel family (gemm_f16_tcgen05), event-timed per launch in ONE EXTRA
-                profiled step after the timed loop (the timed loop itself carries no instrumentation), against MEASURED_PEAKS.json
+  roofline      tensor-core roofline of the dominant kernel family (gemm_f16_tcgen05), event-timed per launch in an extra
+                profiled step after the timed loop (the last of five run back to back, so it sees sustained clocks; the timed
+                loop itself carries no instrumentation), against MEASURED_PEAKS.json
   per_rank_ms_per_step   min / max / argmax over ranks of the device-timed step (the straggler is visible)
   scale_features (N > 1) the feature-extraction step with the cls all-gather (NCCL over NVLink) inside the timed region
   configs (N = 1)        BASELINE.json configs[1], [2], [4] run for a few steps after the headline
@@ -241,12 +242,15 @@ class Workload:
             barrier()
             return e0.elapsed_time(e1), self.eng.kernel_launches - l0
 
-    def profile_one_step(self):
-        """One EXTRA step outside the timed region with an event pair around every kernel (dino_b200_set_profiling)."""
+    def profile_one_step(self, lead_in=4):
+        """Per-kernel event pairs (dino_b200_set_profiling) of ONE step outside the timed region.  `lead_in` profiled steps run
+        back to back right before it, so the measured step sees the same sustained, power-capped clocks as the timed loop (a lone
+        step after an idle gap runs ~12 % faster at burst clocks and would flatter every kernel)."""
         torch = self.torch
         self.eng.set_profiling(True)
         with torch.cuda.stream(self.stream):
-            self.step_device()
+            for _ in range(lead_in + 1):
+                self.step_device()
             self.stream.synchronize()
         prof = self.eng.get_profile()
         self.eng.set_profiling(False)
@@ -512,7 +516,7 @@ def main():
             "config": {"workload": workload, "tokens_per_image": wl.n_tok, "gflop_per_image": fl["total"] / 1e9,
                        "l2_policy": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}", "feature_all_gather": args.gather, "outputs_finite": finite,
-                       "timed_region": "one CUDA-graph replay per step, no per-kernel events (those come from one extra profiled step)"},
+                       "timed_region": "one CUDA-graph replay per step, no per-kernel events (those come from extra profiled steps after the loop)"},
             "clocks": clocks,
             "per_rank_ms_per_step": {"min": min(rank_ms), "max": max(rank_ms), "argmax_rank": int(np.argmax(rank_ms)),
                                      "all": [round(x, 3) for x in rank_ms]},
@@ -528,7 +532,7 @@ def main():
                          "traffic": (traffic["bytes_per_launch"] if traffic else None), "traffic_detail": traffic,
                          "attention_tflops": attn_tflops, "whole_step_tflops": step_tflops,
                          "whole_step_frac_of_burst": step_tflops / peaks["burst"],
-                         "measured_in": "one extra profiled step after the timed loop (direct launches, event pair per kernel)",
+                         "measured_in": "the last of five profiled steps run back to back after the timed loop (direct launches, event pair per kernel, sustained clocks)",
                          "ms_profiled_step": last_prof},
         }
         if scale_features is not None:
