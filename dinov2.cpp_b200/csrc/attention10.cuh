@@ -42,6 +42,20 @@ constexpr int AT10_TILE = 128 * 64 * 2;          // 16 KB: a 128 x 64 fp16 tile
 #ifndef AT10_STAGGER
 #define AT10_STAGGER 0
 #endif
+// 1: the two softmax warpgroups take turns on the exponential phase of a tile (named-barrier baton, as in FlashAttention-3's
+// ping-pong schedule).  One warp per scheduler saturates the XU pipe on its own (85 MUFU.EX2 + 64 F2FP per 128 keys = 1192 cycles,
+// measured 1192); free-running, the warpgroups fall into lock-step within ~10 tiles, exponentiate at the same time (2000-2200
+// cycles each) and leave the pipe idle while both wait for / load / max-reduce their next scores (~900 cycles per tile).
+#ifndef AT10_PINGPONG
+#define AT10_PINGPONG 0     // measured: strict alternation costs 684 us per ViT-L layer against 616 free-running — see DESIGN.md
+#endif
+// 1: fp16 rounding of the MUFU pairs by integer arithmetic instead of F2FP (attn_exp_pairs_ip in attention_softmax.cuh), which
+// takes a third of the work off the XU pipe.  Same accuracy, measured SLOWER (659 vs 634 us per ViT-L layer; without any polynomial
+// pairs 706): two in-order warps per scheduler are bound by their own issue timeline — every instruction added costs, whichever
+// pipe it runs on — not by the XU pipe alone.  Off.
+#ifndef AT10_INTPACK
+#define AT10_INTPACK 0
+#endif
 // 1: chunks that lie entirely beyond the image's last token are neither max-reduced nor exponentiated.  As branches in EVERY tile
 // this measured 7 % slower (724 vs 675 us per ViT-L layer: they cut the body into separate scheduling regions for ptxas); with the
 // tile body specialised per position they only exist in the item's last tile: 647 -> 636 us.
@@ -404,27 +418,44 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         pending = false;                                                                                               \
     } while (0)
 
-#if AT10_STAGGER > 0
-        // start the second warpgroup part of a tile late: with one MMA warp per query tile and no per-item resynchronisation
-        // nothing pulls the two warpgroups back into lock-step, so one of them can feed the MUFU pipe while the other waits
-        // for / loads / max-reduces its next scores
-        if (t == 1) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < AT10_STAGGER) {}
-        }
-#endif
         Attn10Item it;
         it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
         for (int item = item_lo; item < item_hi; ++item, it.step(p.n_qblk, p.n_heads, p.reverse)) {
             if (t == 1 && !it.has_q1(p.n_tok)) continue;
             float m_used = -INFINITY;
             float l_run = 0.f;                            // softmax denominator relative to m_used
+            float l_poly = 0.f;                           // (AT10_INTPACK) its polynomial-pair part; l_run is then in the 2^-112 scale
+#if AT10_PINGPONG
+            // Baton between the warpgroups for the exponential segments of this item (only when both query tiles exist): barrier
+            // 3 = "warpgroup 1 is done, 0 may go", barrier 4 = the reverse.  Every tile is one segment, an item's first tile two
+            // (the previous item's epilogue sits between them, outside the baton).  Warpgroup 1 hands over first and keeps the
+            // baton it would pass after its last segment, so both barriers are balanced per item.
+            const bool pp = it.has_q1(p.n_tok);
+            const int pp_segs = n_kv + 1;
+            int pp_seg = 0;
+            if (pp && t == 1) named_bar_arrive(3, 256);
+            auto baton_take = [&]() {
+                if (pp) named_bar_sync(3 + t, 256);
+            };
+            auto baton_pass = [&]() {
+                ++pp_seg;
+                if (pp && !(t == 1 && pp_seg == pp_segs)) named_bar_arrive(4 - t, 256);
+            };
+#else
+            auto baton_take = [&]() {};
+            auto baton_pass = [&]() {};
+#endif
 
             // One 128-key tile.  The body is instantiated per position in the item — FIRST (sets the reference maximum, hosts the
             // previous item's deferred epilogue), LAST (ragged: keys past the image's last token are masked), middle (neither) —
             // so that the nine middle tiles of an 11-tile item carry no mask / first-tile / epilogue branches: every branch cuts
             // the unrolled body into separate scheduling regions for ptxas and drains the MUFU pipe (measured with three extra
             // branches: 724 vs 675 us per ViT-L layer).
+#if AT10_INTPACK
+#define AT10_EXP(E0, E1, CH, MC) attn_exp_pairs_ip<E0, E1>(CH, pk, c, MC, ls, lp)
+#else
+#define AT10_EXP(E0, E1, CH, MC) attn_exp_pairs<E0, E1>(CH, pk, c, MC, ls)
+#endif
             auto tile = [&](auto first_c, auto last_c) {
                 constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
                 const uint32_t lo = ring + slot * 64;                          // keys 0-63 (P goes back here)
@@ -432,6 +463,12 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 slot = slot == 2 ? 0u : slot + 1;
                 AT10_SEV(10);
                 AT10_PWAIT(6, mbar_wait(&s_full[t], n_tile & 1));
+#if AT10_STAGGER > 0
+                if (t == 1 && n_tile == 0) {                                   // experiment: hold the second warpgroup back once, after its first S has arrived
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < AT10_STAGGER) {}
+                }
+#endif
                 tc_fence_after();
                 AT10_SEV(11);
                 uint32_t c0[32], c1[32], c2[32], c3[32];
@@ -455,13 +492,16 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 if constexpr (FIRST) {
                     m_used = p.n_phantom > 0 ? fmaxf(mx0, 0.f) : mx0;   // O_t is overwritten by the first P V of the item
                     l_run = 0.f;                                        // (phantom keys have score 0: the reference covers them)
+                    l_poly = 0.f;
                 }
+                baton_take();
                 AT10_SEV(14);
                 float ls[2] = {0.f, 0.f};
+                [[maybe_unused]] float lp[2] = {0.f, 0.f};      // (AT10_INTPACK) polynomial pairs, true scale; ls: MUFU pairs, 2^-112 scale
                 uint32_t pk[16];
                 {
                     const float mc = m_used * c;
-                    attn_exp_pairs<0, 8>(c0, pk, c, mc, ls);
+                    AT10_EXP(0, 8, c0, mc);
                     // chunks 1-3 are in registers: S(n)'s second slot may be overwritten -> the MMA warp starts S(n+1)
                     tmem_ld_wait();
                     tc_fence_before();
@@ -486,7 +526,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     }
                     const float mx123 = fmax3(attn_rowmax32(c1), attn_rowmax32(c2), attn_rowmax32(c3));
 #endif
-                    attn_exp_pairs<8, 16>(c0, pk, c, mc, ls);
+                    AT10_EXP(8, 16, c0, mc);
                     tmem_st_32x32b_x16(lo, pk);
                     const float mx = fmaxf(mx0, mx123);
                     const bool grow = mx > m_used + thr;
@@ -495,20 +535,29 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                             mbar_wait(&o_full[t], (n_tile - 1) & 1);
                             tc_fence_after();
                         }
+#if AT10_INTPACK
+                        const bool redo = grow;           // P' = 2^7 P: anything written with a reference more than 2^8 low may exceed fp16
+#else
                         const bool redo = grow && (mx - m_used) * c > 15.0f;
+#endif
                         const float alpha = grow ? ex2_approx((m_used - mx) * c) : 1.0f;
                         if (grow) m_used = mx;
                         l_run *= alpha;
+                        l_poly *= alpha;
                         if (__any_sync(0xffffffffu, redo)) {
                             // chunk 0 again for the whole warp, relative to each lane's (possibly unchanged) reference
                             attn_rescale(o_addr, lo, alpha, !FIRST, 0);
                             ls[0] = 0.f;
                             ls[1] = 0.f;
-                            attn_exp_pairs<0, 16>(c0, pk, c, m_used * c, ls);
+                            lp[0] = 0.f;
+                            lp[1] = 0.f;
+                            AT10_EXP(0, 16, c0, m_used * c);
                             tmem_st_32x32b_x16(lo, pk);
                         } else {
                             ls[0] *= alpha;
                             ls[1] *= alpha;
+                            lp[0] *= alpha;
+                            lp[1] *= alpha;
                             attn_rescale(o_addr, lo, alpha, !FIRST, 16);
                         }
                     }
@@ -517,48 +566,52 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     const float mc = m_used * c;
 #if AT10_SKIP_MASKED
                     if (kv_valid > 32) {
-                        attn_exp_pairs<0, 16>(c1, pk, c, mc, ls);
+                        AT10_EXP(0, 16, c1, mc);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
 #else
-                    attn_exp_pairs<0, 16>(c1, pk, c, mc, ls);
+                    AT10_EXP(0, 16, c1, mc);
 #endif
                     tmem_st_32x32b_x16(lo + 16, pk);
                     // The previous item's output: O_t stays untouched until this tile's P V, which is issued only after the
                     // p_full arrive below.  64 score registers (chunks 0 and 1) are free at this point.
                     if constexpr (FIRST) {
+                        baton_pass();
                         if (pending) {
                             AT10_SEV(18);
                             AT10_PWAIT(10, AT10_EPILOGUE());
                             AT10_SEV(19);
                         }
+                        baton_take();
                     }
 #if AT10_SKIP_MASKED
                     if (kv_valid > 64) {
-                        attn_exp_pairs<0, 16>(c2, pk, c, mc, ls);
+                        AT10_EXP(0, 16, c2, mc);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
 #else
-                    attn_exp_pairs<0, 16>(c2, pk, c, mc, ls);
+                    AT10_EXP(0, 16, c2, mc);
 #endif
                     tmem_st_32x32b_x16(lo + 32, pk);
 #if AT10_SKIP_MASKED
                     if (kv_valid > 96) {
-                        attn_exp_pairs<0, 16>(c3, pk, c, mc, ls);
+                        AT10_EXP(0, 16, c3, mc);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
 #else
-                    attn_exp_pairs<0, 16>(c3, pk, c, mc, ls);
+                    AT10_EXP(0, 16, c3, mc);
 #endif
                     tmem_st_32x32b_x16(lo + 48, pk);
                 }
+                baton_pass();
                 l_run += ls[0] + ls[1];
+                l_poly += lp[0] + lp[1];
                 AT10_SEV(15);
                 // (Announcing P(n) only at the top of tile n+1, under the load of its first scores, measured 1.3 % slower: the
                 // P V it delays is what the MMA warp issues before the S after next.)
@@ -579,8 +632,13 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 tile(no_t{}, yes_t{});
             }
             pending = true;
+#if AT10_INTPACK
+            if (p.n_phantom > 0) l_poly += static_cast<float>(p.n_phantom) * ex2_approx(ATS_IP_SHIFT - m_used * c);   // the zero keys of the -fa path
+            pend_l = fmaf(l_run, ATS_IP_UNBIAS, l_poly);
+#else
             if (p.n_phantom > 0) l_run += static_cast<float>(p.n_phantom) * ex2_approx(-m_used * c);   // the zero keys of the -fa path
             pend_l = l_run;
+#endif
             pend_c0 = it.head * 64;
             pend_c1 = it.qb * 256 + t * 128;
             pend_c2 = it.img;
@@ -609,5 +667,6 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
 #undef AT10_SEV
 #undef AT10_ISSUE_S
 #undef AT10_EPILOGUE
+#undef AT10_EXP
 
 }  // namespace dino

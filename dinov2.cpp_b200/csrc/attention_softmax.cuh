@@ -170,4 +170,74 @@ __device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t
 #endif
 }
 
+// The same with the fp16 rounding of the MUFU pairs moved off the XU pipe (attention10.cuh, AT10_INTPACK).  F2FP runs on the
+// XU pipe like MUFU.EX2, 8 cycles per warp instruction: one pack per two exponentials made it a third of the pipe that bounds
+// the kernel.  Here probabilities are produced as P' = 2^7 P, and for a MUFU pair the exponent argument carries a further -112,
+// i.e. MUFU returns v = P' 2^-112: the fp32 exponent field of v IS the fp16 exponent field of P' (127 - 112 = 15), so
+//     fp16(P') = (bits(v) + 0x1000) >> 13          (round half up; fp32-denormal v would map onto fp16 denormals, .ftz drops them:
+//                                                   P' < 2^-14, i.e. P < 2^-21 of the reference maximum, is zero)
+// and two of them are packed with IMAD, IMAD, PRMT: hi16(bits * 8 + 0x8000).  The 2^7 puts the flush threshold at 2^-21 instead
+// of 2^-14 (fp16 denormals reach 2^-24); lazily referenced probabilities stay <= 2^15 < 65504 as long as growth beyond 2^8 is
+// re-exponentiated (attention10.cuh does).  Polynomial pairs are built in true scale (P', cubic + exponent patch as above) and
+// still packed with F2FP: their clamp at 2^-30 needs the rounding to reach zero for masked keys.
+// Row sums: `ls` accumulates the MUFU pairs in the v scale (multiply by 2^112 at the end), `lp` the polynomial pairs in P' scale.
+constexpr float ATS_IP_SHIFT = 7.0f;               // P' = 2^7 P
+constexpr float ATS_IP_BIAS = 112.0f - 7.0f;       // MUFU pairs: exponent argument offset so that v = P' 2^-112
+constexpr float ATS_IP_UNBIAS = 5.192296858534828e33f;   // 2^112
+template <int E0, int E1>
+__device__ __forceinline__ void attn_exp_pairs_ip(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2], float (&lp)[2]) {
+    const f32x2 c2 = pack_f32x2(c, c);
+    const f32x2 nmc_m = pack_f32x2(-(mc + ATS_IP_BIAS), -(mc + ATS_IP_BIAS)), nmc_p = pack_f32x2(ATS_IP_SHIFT - mc, ATS_IP_SHIFT - mc);
+    f32x2 acc_m = pack_f32x2(ls[0], ls[1]), acc_p = pack_f32x2(lp[0], lp[1]);
+    float q0[E1 - E0], q1[E1 - E0];
+    constexpr int PM = ATS_POLY_MOD > 0 ? ATS_POLY_MOD : 1;
+#pragma unroll
+    for (int e = E0; e < E1 + ATS_PIPE; ++e) {
+        if (e < E1) {
+            const bool poly = ATS_POLY_MOD > 0 && (e % PM) == PM - 1;
+            const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, poly ? nmc_p : nmc_m);
+            float p0, p1;
+            if (poly) {
+                float x0, x1;
+                unpack_f32x2(x, x0, x1);
+                const f32x2 t = pack_f32x2(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
+                const f32x2 magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+                const f32x2 u = add2_f32(t, magic);
+                const f32x2 w = add2_f32(u, nmagic);
+                float w0, w1;
+                unpack_f32x2(w, w0, w1);
+                const f32x2 f = add2_f32(t, pack_f32x2(-w0, -w1));
+                f32x2 q = fma2_f32(pack_f32x2(0.05508868396282196f, 0.05508868396282196f), f, pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+                q = fma2_f32(q, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+                q = fma2_f32(q, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+                float r0, r1, u0, u1;
+                unpack_f32x2(q, r0, r1);
+                unpack_f32x2(u, u0, u1);
+                p0 = __int_as_float(__float_as_int(r0) + (__float_as_int(u0) << 23));
+                p1 = __int_as_float(__float_as_int(r1) + (__float_as_int(u1) << 23));
+            } else {
+                float x0, x1;
+                unpack_f32x2(x, x0, x1);
+                p0 = ex2_approx_ordered(x0);
+                p1 = ex2_approx_ordered(x1);
+            }
+            q0[e - E0] = p0;
+            q1[e - E0] = p1;
+        }
+        if (e - ATS_PIPE >= E0) {
+            const int d = e - ATS_PIPE;
+            const bool poly = ATS_POLY_MOD > 0 && (d % PM) == PM - 1;
+            if (poly) {
+                acc_p = add2_f32_ordered(acc_p, pack_f32x2(q0[d - E0], q1[d - E0]));
+                pk[d] = cvt_f16x2(q0[d - E0], q1[d - E0]);
+            } else {
+                acc_m = add2_f32_ordered(acc_m, pack_f32x2(q0[d - E0], q1[d - E0]));
+                pk[d] = __byte_perm(__float_as_uint(q0[d - E0]) * 8u + 0x8000u, __float_as_uint(q1[d - E0]) * 8u + 0x8000u, 0x7632);
+            }
+        }
+    }
+    unpack_f32x2(acc_m, ls[0], ls[1]);
+    unpack_f32x2(acc_p, lp[0], lp[1]);
+}
+
 }  // namespace dino
