@@ -34,11 +34,23 @@
 
 namespace dino {
 
-constexpr int AT10_THREADS = 384;
+// AT10_SPLIT = 1: TWO THREADS PER QUERY ROW.  Four softmax warpgroups instead of two: warps 0-3 / 4-7 take keys 0-63 of every
+// 128-key tile of query tile 0 / 1, warps 8-11 / 12-15 keys 64-127 (TMEM lane quarter = warp & 3 either way).  The two halves of a
+// row agree on the reference maximum through shared memory once per tile (one named barrier per query tile), keep separate row
+// sums and each own 32 of the 64 output columns.  Why: with one thread per row there are two softmax warps per scheduler, each
+// an in-order stream of ~85 MUFU (8-cycle dispatch) + ~600 other instructions per tile — the XU, FMA and ALU pipes idle in turn.
+// Four warps per scheduler with half the work each overlap those streams.  Helper warps move to 16-19.
+#ifndef AT10_SPLIT
+#define AT10_SPLIT 0
+#endif
+constexpr int AT10_HW = AT10_SPLIT ? 16 : 8;     // first helper warp: +0 TMEM allocator, +1 TMA producer, +2 / +3 MMA issuers of query tile 1 / 0
+constexpr int AT10_THREADS = (AT10_HW + 4) * 32;
+constexpr int AT10_SM_THREADS = AT10_SPLIT ? 256 : 128;   // softmax threads per query tile
 constexpr int AT10_TILE = 128 * 64 * 2;          // 16 KB: a 128 x 64 fp16 tile
 #ifndef AT10_KV_STAGES
-#define AT10_KV_STAGES 4
+#define AT10_KV_STAGES (AT10_SPLIT ? 3 : 4)      // 3 measured equal to 4 (619 vs 620 us); the split variant needs the space for its exchange buffers
 #endif
+constexpr int AT10_XCHG_BYTES = AT10_SPLIT ? 2 * 2 * 2 * 128 * 4 : 0;   // [max | sum][query tile][half][row] floats
 #ifndef AT10_STAGGER
 #define AT10_STAGGER 0
 #endif
@@ -63,7 +75,7 @@ constexpr int AT10_TILE = 128 * 64 * 2;          // 16 KB: a 128 x 64 fp16 tile
 #define AT10_SKIP_MASKED 1
 #endif
 // Q: 2 buffers x 2 tiles; K, V: stages; O staging: 2 tiles; barriers; alignment slack
-constexpr int AT10_SMEM_BYTES = 4 * AT10_TILE + AT10_KV_STAGES * 2 * AT10_TILE + 2 * AT10_TILE + 256 + 1024;
+constexpr int AT10_SMEM_BYTES = 4 * AT10_TILE + AT10_KV_STAGES * 2 * AT10_TILE + 2 * AT10_TILE + 256 + AT10_XCHG_BYTES + 1024;
 constexpr float AT10_RESCALE_LOG2 = 8.0f;        // lazy-rescale threshold in the exp2 domain
 
 // Optional cycle trace of CTA 0 (compile with -DAT10_TRACE): (event id, index, clock) per role, written to p.trace
@@ -174,6 +186,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     uint64_t *p_full = s_free + 2;                        // 2 x 2
     uint64_t *o_full = p_full + 4;                        // 2: P_t(n) V has completed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(o_full + 2);
+    [[maybe_unused]] float *xchg = reinterpret_cast<float *>(sO + 2 * AT10_TILE + 256);   // (AT10_SPLIT) [kind][query tile][half][row]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -187,11 +200,11 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     long long prof_acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
 #endif
-    if (warp == 9 && lane == 0) {
+    if (warp == AT10_HW + 1 && lane == 0) {
         prefetch_tmap(&tmQKV);
         prefetch_tmap(&tmOut);
     }
-    if (warp == 11 && lane == 0) {
+    if (warp == AT10_HW + 3 && lane == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&q_full[b], 1);
             mbar_init(&q_empty[b], 2);                    // both MMA warps have issued their last Q K^T of the item
@@ -202,14 +215,14 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
-            mbar_init(&s_free[t], 128);
-            mbar_init(&p_full[2 * t], 128);
-            mbar_init(&p_full[2 * t + 1], 128);
+            mbar_init(&s_free[t], AT10_SM_THREADS);
+            mbar_init(&p_full[2 * t], AT10_SM_THREADS);
+            mbar_init(&p_full[2 * t + 1], AT10_SM_THREADS);
             mbar_init(&o_full[t], 1);
         }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    if (warp == AT10_HW) tmem_alloc(tmem_ptr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -219,9 +232,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     griddep_wait();                              // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
     griddep_launch_dependents();
 
-    if (warp >= 8) {
-        setmaxnreg_dec<80>();
-        if (warp == 9 && item_lo < item_hi) {
+    if (warp >= AT10_HW) {
+        setmaxnreg_dec<AT10_SPLIT ? 64 : 80>();
+        if (warp == AT10_HW + 1 && item_lo < item_hi) {
             // ---------------------------------------------------------------- TMA producer (warp-uniform; one lane issues)
             int s = 0;
             uint32_t ph = 0, li = 0;                       // K/V stage + phase; local item index (Q buffer = li & 1)
@@ -249,13 +262,13 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     if (++s == AT10_KV_STAGES) { s = 0; ph ^= 1; }
                 }
             }
-        } else if (warp >= 10 && item_lo < item_hi) {
+        } else if (warp >= AT10_HW + 2 && item_lo < item_hi) {
             // ---------------------------------------------------------------- MMA issuers: warp 11 -> query tile 0, warp 10 -> tile 1
             // All 32 lanes run the control flow, barrier waits and descriptor arithmetic (warp-uniform -> uniform
             // datapath); one elected lane issues tcgen05.mma / tcgen05.commit.  Both warps walk every item and tile; the
             // tile-1 warp skips the MMAs of items without a second query tile but still takes part in the stage / Q-buffer
             // hand-backs (a commit with nothing outstanding arrives at once).
-            const int T = 11 - warp;
+            const int T = AT10_HW + 3 - warp;
             constexpr uint32_t idesc_s128 = make_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_s64 = make_idesc_f16(128, 64, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);     // A = P (TMEM), B = V, MN-major
@@ -363,6 +376,190 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             }
         }
     } else {
+#if AT10_SPLIT
+        // ---------------------------------------------------------------- softmax, two threads per query row (see AT10_SPLIT above)
+        setmaxnreg_inc<104>();
+        const int t = (warp >> 2) & 1;                    // query tile
+        const int h = warp >> 3;                          // key half of every 128-key tile (and output-column half of the row)
+        const int qd = warp & 3;                          // TMEM lane quarter
+        const int r = qd * 32 + lane;                     // row inside the tile
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t ring = tmem_R + lane_addr + t * 192;
+        const uint32_t o_addr = tmem_O + lane_addr + t * 64 + 32 * h;        // this thread's 32 of the row's 64 output columns
+        const float c = p.scale_log2;
+        const float thr = AT10_RESCALE_LOG2 / c;
+        uint32_t n_tile = 0;
+        uint32_t slot = 0;
+        [[maybe_unused]] int tr_n = 0;
+        uint8_t *stage_row = sO + t * AT10_TILE + r * 128;
+        const uint32_t sw = static_cast<uint32_t>(r & 7);
+        const bool tile_leader = h == 0 && (threadIdx.x & 127) == 0;         // issues the TMA store of query tile t
+        float *xmax_own = xchg + ((0 * 2 + t) * 2 + h) * 128 + r, *xmax_other = xchg + ((0 * 2 + t) * 2 + (1 - h)) * 128 + r;
+        float *xsum_own = xchg + ((1 * 2 + t) * 2 + h) * 128 + r, *xsum_other = xchg + ((1 * 2 + t) * 2 + (1 - h)) * 128 + r;
+#define AT10_SEV(ID) do { if (tile_leader) AT10_EV(1 + t, ID, n_tile); } while (0)
+        bool pending = false;
+        float pend_l = 1.f;
+        int pend_c0 = 0, pend_c1 = 0, pend_c2 = 0;
+// This half's 32 columns of O_t / (row sum of both halves) -> fp16 -> its 64 bytes of the row in the swizzled staging tile;
+// one TMA store per query tile.  The two barriers also order the exchange of the halves' row sums.
+#define AT10_EPILOGUE()                                                                                                \
+    do {                                                                                                               \
+        AT10_PWAIT(7, mbar_wait(&o_full[t], (n_tile - 1) & 1));                                                        \
+        tc_fence_after();                                                                                              \
+        uint32_t a__[32];                                                                                              \
+        tmem_ld_32x32b_x32(o_addr, a__);                                                                               \
+        tmem_ld_wait();                                                                                                \
+        tc_fence_before();                                                                                             \
+        *xsum_own = pend_l;                                                                                            \
+        if (tile_leader) bulk_wait_read<0>();    /* the previous store has finished reading the staging tile */        \
+        named_bar_sync(1 + t, 256);                                                                                    \
+        const float inv__ = 1.0f / (pend_l + *xsum_other);                                                             \
+        _Pragma("unroll") for (int v = 0; v < 4; ++v) {                                                                \
+            *reinterpret_cast<uint4 *>(stage_row + ((static_cast<uint32_t>(v + 4 * h) ^ sw) << 4)) =                   \
+                make_uint4(pack_half2(__uint_as_float(a__[8 * v]) * inv__, __uint_as_float(a__[8 * v + 1]) * inv__),   \
+                           pack_half2(__uint_as_float(a__[8 * v + 2]) * inv__, __uint_as_float(a__[8 * v + 3]) * inv__), \
+                           pack_half2(__uint_as_float(a__[8 * v + 4]) * inv__, __uint_as_float(a__[8 * v + 5]) * inv__), \
+                           pack_half2(__uint_as_float(a__[8 * v + 6]) * inv__, __uint_as_float(a__[8 * v + 7]) * inv__)); \
+        }                                                                                                              \
+        fence_proxy_async_smem();                                                                                      \
+        named_bar_sync(1 + t, 256);                                                                                    \
+        if (tile_leader) {                                                                                             \
+            tma_store_3d(&tmOut, sO + t * AT10_TILE, pend_c0, pend_c1, pend_c2);                                       \
+            bulk_commit();                                                                                             \
+        }                                                                                                              \
+        pending = false;                                                                                               \
+    } while (0)
+
+        Attn10Item it;
+        it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
+        for (int item = item_lo; item < item_hi; ++item, it.step(p.n_qblk, p.n_heads, p.reverse)) {
+            if (t == 1 && !it.has_q1(p.n_tok)) continue;
+            float m_used = -INFINITY;
+            float l_run = 0.f;                            // this half's part of the softmax denominator, relative to m_used
+            [[maybe_unused]] float l_poly = 0.f;          // (AT10_INTPACK) its polynomial-pair part; l_run is then in the 2^-112 scale
+#if AT10_INTPACK
+#define AT10_EXP(E0, E1, CH, MC) attn_exp_pairs_ip<E0, E1>(CH, pk, c, MC, ls, lp)
+#else
+#define AT10_EXP(E0, E1, CH, MC) attn_exp_pairs<E0, E1>(CH, pk, c, MC, ls)
+#endif
+            auto tile = [&](auto first_c, auto last_c) {
+                constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
+                const uint32_t lo = ring + slot * 64;                          // keys 0-63 (P of the whole tile goes back here)
+                const uint32_t hi = ring + (slot == 2 ? 0u : slot + 1) * 64;   // keys 64-127
+                slot = slot == 2 ? 0u : slot + 1;
+                const uint32_t src = h ? hi : lo;                              // this half's 64 scores
+                const uint32_t pdst = lo + 32 * h;                             // this half's 32 columns of packed P
+                AT10_SEV(10);
+                AT10_PWAIT(6, mbar_wait(&s_full[t], n_tile & 1));
+                tc_fence_after();
+                AT10_SEV(11);
+                uint32_t c0[32], c1[32];
+                tmem_ld_32x32b_x32(src, c0);
+                tmem_ld_32x32b_x32(src + 32, c1);
+                tmem_ld_wait();
+                AT10_SEV(12);
+                // keys of this half that exist (only an item's last tile is ragged; <= 0: the whole half lies beyond the image)
+                const int kv_valid = LAST ? p.n_tok - (n_kv - 1) * 128 - 64 * h : 64;
+                if constexpr (LAST) {
+                    if (kv_valid < 32) attn_mask32(c0, kv_valid);
+                    if (kv_valid < 64) attn_mask32(c1, kv_valid - 32);
+                }
+                // the row's maximum over all 128 keys: exchanged with the thread that holds the other half.  s_free is announced
+                // only after the partner's value has been read, so its next write (after S(n+1), which waits for s_free) cannot
+                // overtake this read; the barrier also keeps the P columns written below from clobbering scores the partner
+                // has not loaded yet (P of keys 64-127 lands on the columns of the scores of keys 32-63).
+                const float mxh = fmaxf(attn_rowmax32(c0), attn_rowmax32(c1));
+                *xmax_own = mxh;
+                named_bar_sync(5 + t, 256);
+                const float mx = fmaxf(mxh, *xmax_other);
+                tc_fence_before();
+                mbar_arrive(&s_free[t]);
+                if constexpr (FIRST) {
+                    m_used = p.n_phantom > 0 ? fmaxf(mx, 0.f) : mx;
+                    l_run = 0.f;
+                    l_poly = 0.f;
+                } else {
+                    const bool grow = mx > m_used + thr;
+                    if (__any_sync(0xffffffffu, grow)) {  // rare: O_t (this half's columns) and the sum move down to the new reference
+                        mbar_wait(&o_full[t], (n_tile - 1) & 1);      // O_t must be quiescent, i.e. P(n-1) V(n-1) complete
+                        tc_fence_after();
+                        const float alpha = grow ? ex2_approx((m_used - mx) * c) : 1.0f;
+                        if (grow) m_used = mx;
+                        l_run *= alpha;
+                        l_poly *= alpha;
+#pragma unroll 1
+                        for (int i = 0; i < 32; i += 8) {
+                            uint32_t a[8];
+                            tmem_ld_32x32b_x8(o_addr + i, a);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int d = 0; d < 8; ++d) a[d] = __float_as_uint(__uint_as_float(a[d]) * alpha);
+                            tmem_st_32x32b_x8(o_addr + i, a);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                AT10_SEV(14);
+                float ls[2] = {0.f, 0.f};
+                [[maybe_unused]] float lp[2] = {0.f, 0.f};
+                uint32_t pk[16];
+                const float mc = m_used * c;
+                if (!LAST || kv_valid > 0) {
+                    AT10_EXP(0, 16, c0, mc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+                tmem_st_32x32b_x16(pdst, pk);
+                // the previous item's output: O_t stays untouched until this tile's P V, issued only after the p_full arrive below
+                if constexpr (FIRST) {
+                    if (pending) {
+                        AT10_SEV(18);
+                        AT10_PWAIT(10, AT10_EPILOGUE());
+                        AT10_SEV(19);
+                    }
+                }
+                if (!LAST || kv_valid > 32) {
+                    AT10_EXP(0, 16, c1, mc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+                tmem_st_32x32b_x16(pdst + 16, pk);
+                l_run += ls[0] + ls[1];
+                l_poly += lp[0] + lp[1];
+                AT10_SEV(15);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[2 * t + (n_tile & 1)]);
+                AT10_SEV(17);
+                ++n_tile;
+            };
+            using yes_t = std::integral_constant<bool, true>;
+            using no_t = std::integral_constant<bool, false>;
+            if (n_kv == 1) {
+                tile(yes_t{}, yes_t{});
+            } else {
+                tile(yes_t{}, no_t{});
+#pragma unroll 1
+                for (int j = 1; j + 1 < n_kv; ++j) tile(no_t{}, no_t{});
+                tile(no_t{}, yes_t{});
+            }
+            pending = true;
+#if AT10_INTPACK
+            if (p.n_phantom > 0 && h == 0) l_poly += static_cast<float>(p.n_phantom) * ex2_approx(ATS_IP_SHIFT - m_used * c);   // the zero keys of the -fa path
+            pend_l = fmaf(l_run, ATS_IP_UNBIAS, l_poly);
+#else
+            if (p.n_phantom > 0 && h == 0) l_run += static_cast<float>(p.n_phantom) * ex2_approx(-m_used * c);   // the zero keys of the -fa path
+            pend_l = l_run;
+#endif
+            pend_c0 = it.head * 64;
+            pend_c1 = it.qb * 256 + t * 128;
+            pend_c2 = it.img;
+        }
+        if (pending) AT10_EPILOGUE();
+        if (tile_leader) bulk_wait<0>();                  // the staging tile must outlive the last TMA store
+#else
         setmaxnreg_inc<208>();
         const int t = warp >> 2;                          // query tile / warpgroup
         const int qd = warp & 3;                          // TMEM lane quarter
@@ -645,20 +842,21 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         }
         if (pending) AT10_EPILOGUE();
         if (wg_leader) bulk_wait<0>();                    // the staging tile must outlive the last TMA store
+#endif
     }
 
 #ifdef AT10_PROF
     if (blockIdx.x == 0 && p.trace && lane == 0) {
         const long long tot = clock64() - prof_t0;
-        if (warp == 9) { p.trace[0] = prof_acc[0]; p.trace[1] = prof_acc[1]; }
-        if (warp == 11) { p.trace[2] = prof_acc[2]; p.trace[3] = prof_acc[3]; p.trace[4] = prof_acc[4]; p.trace[5] = prof_acc[5]; p.trace[9] = tot; }
+        if (warp == AT10_HW + 1) { p.trace[0] = prof_acc[0]; p.trace[1] = prof_acc[1]; }
+        if (warp == AT10_HW + 3) { p.trace[2] = prof_acc[2]; p.trace[3] = prof_acc[3]; p.trace[4] = prof_acc[4]; p.trace[5] = prof_acc[5]; p.trace[9] = tot; }
         if (warp == 0) { p.trace[6] = prof_acc[6]; p.trace[7] = prof_acc[7]; p.trace[8] = tot; p.trace[10] = prof_acc[10]; }
     }
 #endif
     griddep_launch_dependents_late();
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == AT10_HW) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
