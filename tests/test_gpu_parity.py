@@ -230,6 +230,39 @@ def test_pipelined_submit_wait_matches_synchronous_forward(workdir):
                 assert np.array_equal(outs[k][name], want[k][name]), (k, name)
 
 
+_FUSE_LN_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import dinov2_b200 as d
+from dinov2_b200 import synth
+imgs = synth.lcg_batch(0, int(sys.argv[4]), 518, 518)
+with d.Engine(sys.argv[2]) as e:
+    out = e.forward(imgs, classify=True)
+np.savez(sys.argv[3], **out)
+"""
+
+
+@pytest.mark.parametrize("name,B", [("vits14_reg4", 3), ("vitb14", 2)])
+def test_forward_with_fused_layernorm_is_bit_identical(name, B, workdir):
+    """DINO_B200_FUSE_LN=1 runs norm2 / the next block's norm1 inside the residual GEMMs (EPI_RESID_LN_F32, LayerNorm worker
+    warps).  The option is off by default but must stay exact: same X bits (same TMA reduce-adds), same row
+    arithmetic as the stand-alone kernel -> every output of the forward pass is bit-identical.  The switch is read once per
+    process, so both variants run in children."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(workdir, f"fuse_{name}.gguf")
+    synth.write_synth_gguf(path, synth.CONFIGS[name], seed=5)
+    outs = {}
+    for flag in ("0", "1"):
+        npz = os.path.join(workdir, f"fuse_{name}_{flag}.npz")
+        env = dict(os.environ, DINO_B200_FUSE_LN=flag)
+        subprocess.run([sys.executable, "-c", _FUSE_LN_CHILD, root, path, npz, str(B)], check=True, env=env, timeout=300)
+        outs[flag] = dict(np.load(npz))
+    for k in outs["0"]:
+        assert np.array_equal(outs["0"][k], outs["1"][k]), k
+    assert np.isfinite(outs["1"]["logits"]).all()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Full-size parity on every BASELINE.json config, against the reference itself (oracle/_ref: the unmodified reference
 # built from /root/reference, running live on this box's host cores).  The engine runs the WHOLE batch of the config;
