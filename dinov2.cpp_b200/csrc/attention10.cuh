@@ -442,6 +442,24 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
 #else
 #define AT10_EXP(E0, E1, CH, MC) attn_exp_pairs<E0, E1>(CH, pk, c, MC, ls)
 #endif
+#if AT10_PINGPONG
+            // baton between the two query tiles for the exponential segments (see the one-thread-per-row path below): all four
+            // warpgroups take part, the two of a query tile take and pass together
+            const bool pp = it.has_q1(p.n_tok);
+            const int pp_segs = n_kv + 1;
+            int pp_seg = 0;
+            if (pp && t == 1) named_bar_arrive(3, 512);
+            auto baton_take = [&]() {
+                if (pp) named_bar_sync(3 + t, 512);
+            };
+            auto baton_pass = [&]() {
+                ++pp_seg;
+                if (pp && !(t == 1 && pp_seg == pp_segs)) named_bar_arrive(4 - t, 512);
+            };
+#else
+            auto baton_take = [&]() {};
+            auto baton_pass = [&]() {};
+#endif
             auto tile = [&](auto first_c, auto last_c) {
                 constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
                 const uint32_t lo = ring + slot * 64;                          // keys 0-63 (P of the whole tile goes back here)
@@ -499,6 +517,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                         tmem_st_wait();
                     }
                 }
+                baton_take();
                 AT10_SEV(14);
                 float ls[2] = {0.f, 0.f};
                 [[maybe_unused]] float lp[2] = {0.f, 0.f};
@@ -513,11 +532,13 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 tmem_st_32x32b_x16(pdst, pk);
                 // the previous item's output: O_t stays untouched until this tile's P V, issued only after the p_full arrive below
                 if constexpr (FIRST) {
+                    baton_pass();
                     if (pending) {
                         AT10_SEV(18);
                         AT10_PWAIT(10, AT10_EPILOGUE());
                         AT10_SEV(19);
                     }
+                    baton_take();
                 }
                 if (!LAST || kv_valid > 32) {
                     AT10_EXP(0, 16, c1, mc);
@@ -526,6 +547,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     for (int i = 0; i < 16; ++i) pk[i] = 0u;
                 }
                 tmem_st_32x32b_x16(pdst + 16, pk);
+                baton_pass();
                 l_run += ls[0] + ls[1];
                 l_poly += lp[0] + lp[1];
                 AT10_SEV(15);
