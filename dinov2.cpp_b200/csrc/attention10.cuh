@@ -187,6 +187,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     uint64_t *o_full = p_full + 4;                        // 2: P_t(n) V has completed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(o_full + 2);
     [[maybe_unused]] float *xchg = reinterpret_cast<float *>(sO + 2 * AT10_TILE + 256);   // (AT10_SPLIT) [kind][query tile][half][row]
+    // (AT10_SPLIT) the two warps that share 32 query rows (same query tile and lane quarter, key halves 0 / 1) meet here once per tile
+    [[maybe_unused]] uint64_t *pair_bar = reinterpret_cast<uint64_t *>(tmem_ptr + 2);     // [query tile][lane quarter], 64 arrivals
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -220,6 +222,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             mbar_init(&p_full[2 * t + 1], AT10_SM_THREADS);
             mbar_init(&o_full[t], 1);
         }
+#if AT10_SPLIT
+        for (int i = 0; i < 8; ++i) mbar_init(&pair_bar[i], 64);
+#endif
         fence_mbar_init();
     }
     if (warp == AT10_HW) tmem_alloc(tmem_ptr, 512);
@@ -448,13 +453,16 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             const bool pp = it.has_q1(p.n_tok);
             const int pp_segs = n_kv + 1;
             int pp_seg = 0;
-            if (pp && t == 1) named_bar_arrive(3, 512);
+            // one baton PER SCHEDULER (lane quarter qd = warp & 3 = the SM sub-partition the warp lives on): the XU pipe is shared per
+            // sub-partition, and a baton over all warps of a query tile waits for the slowest of its eight warps (hand-over ~285
+            // cycles measured).  Barriers 7 + qd: "tile 1 is done here, tile 0 may go", 11 + qd: the reverse; 128 threads each.
+            if (pp && t == 1) named_bar_arrive(7 + qd, 128);
             auto baton_take = [&]() {
-                if (pp) named_bar_sync(3 + t, 512);
+                if (pp) named_bar_sync((t == 0 ? 7 : 11) + qd, 128);
             };
             auto baton_pass = [&]() {
                 ++pp_seg;
-                if (pp && !(t == 1 && pp_seg == pp_segs)) named_bar_arrive(4 - t, 512);
+                if (pp && !(t == 1 && pp_seg == pp_segs)) named_bar_arrive((t == 0 ? 11 : 7) + qd, 128);
             };
 #else
             auto baton_take = [&]() {};
@@ -482,13 +490,15 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     if (kv_valid < 32) attn_mask32(c0, kv_valid);
                     if (kv_valid < 64) attn_mask32(c1, kv_valid - 32);
                 }
-                // the row's maximum over all 128 keys: exchanged with the thread that holds the other half.  s_free is announced
+                // the row's maximum over all 128 keys: exchanged with the thread that holds the other half (the two warps of a lane
+                // quarter meet on an mbarrier: a named barrier over the query tile's eight warps waits for the slowest).  s_free is announced
                 // only after the partner's value has been read, so its next write (after S(n+1), which waits for s_free) cannot
                 // overtake this read; the barrier also keeps the P columns written below from clobbering scores the partner
                 // has not loaded yet (P of keys 64-127 lands on the columns of the scores of keys 32-63).
                 const float mxh = fmaxf(attn_rowmax32(c0), attn_rowmax32(c1));
                 *xmax_own = mxh;
-                named_bar_sync(5 + t, 256);
+                mbar_arrive(&pair_bar[t * 4 + qd]);
+                mbar_wait(&pair_bar[t * 4 + qd], n_tile & 1);
                 const float mx = fmaxf(mxh, *xmax_other);
                 tc_fence_before();
                 mbar_arrive(&s_free[t]);
