@@ -184,6 +184,11 @@ __device__ __forceinline__ void attn_exp_pairs(const uint32_t (&v)[32], uint32_t
 constexpr float ATS_IP_SHIFT = 7.0f;               // P' = 2^7 P
 constexpr float ATS_IP_BIAS = 112.0f - 7.0f;       // MUFU pairs: exponent argument offset so that v = P' 2^-112
 constexpr float ATS_IP_UNBIAS = 5.192296858534828e33f;   // 2^112
+// ATS_IP_MOD: only every ATS_IP_MOD-th pair is packed by integer arithmetic (1 = every MUFU pair), the others keep F2FP in true
+// scale like the polynomial pairs — a way to balance the XU pipe (MUFU + F2FP) against the ALU pipe (LEA, LEA, PRMT).
+#ifndef ATS_IP_MOD
+#define ATS_IP_MOD 1
+#endif
 template <int E0, int E1>
 __device__ __forceinline__ void attn_exp_pairs_ip(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float mc, float (&ls)[2], float (&lp)[2]) {
     const f32x2 c2 = pack_f32x2(c, c);
@@ -195,7 +200,8 @@ __device__ __forceinline__ void attn_exp_pairs_ip(const uint32_t (&v)[32], uint3
     for (int e = E0; e < E1 + ATS_PIPE; ++e) {
         if (e < E1) {
             const bool poly = ATS_POLY_MOD > 0 && (e % PM) == PM - 1;
-            const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, poly ? nmc_p : nmc_m);
+            const bool ip = !poly && (e % ATS_IP_MOD) == 0;          // integer pack (v scale); otherwise true scale + F2FP
+            const f32x2 x = fma2_f32(pack_f32x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, ip ? nmc_m : nmc_p);
             float p0, p1;
             if (poly) {
                 float x0, x1;
@@ -227,7 +233,8 @@ __device__ __forceinline__ void attn_exp_pairs_ip(const uint32_t (&v)[32], uint3
         if (e - ATS_PIPE >= E0) {
             const int d = e - ATS_PIPE;
             const bool poly = ATS_POLY_MOD > 0 && (d % PM) == PM - 1;
-            if (poly) {
+            const bool ip = !poly && (d % ATS_IP_MOD) == 0;
+            if (!ip) {
                 acc_p = add2_f32_ordered(acc_p, pack_f32x2(q0[d - E0], q1[d - E0]));
                 pk[d] = cvt_f16x2(q0[d - E0], q1[d - E0]);
             } else {
