@@ -461,6 +461,11 @@ def main():
             mine = torch.empty(B * world, fw.D, device="cuda")
             ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(mine.data_ptr()), ctypes.c_void_p(gbuf), B * world * fw.D * 4, 3)
             same = bool(torch.equal(mine, g_out))
+            if not same:   # which source rank's rows differ on this rank, and by how much (stderr: stdout is the JSON line)
+                bad = [int((mine[r * B:(r + 1) * B] != g_out[r * B:(r + 1) * B]).any(dim=-1).sum()) for r in range(world)]
+                print(f"[gather check] rank {rank}: rows differing per source rank {bad}, max |diff| "
+                      f"{float((mine - g_out).abs().max()):.3e}, finite {bool(torch.isfinite(mine).all())}/{bool(torch.isfinite(g_out).all())}",
+                      file=sys.stderr, flush=True)
             flags = torch.tensor([1.0 if same else 0.0], device="cuda")
             dist.all_reduce(flags, op=dist.ReduceOp.MIN)
             scale_features["fused_peer_store"] = {"value": B * world * n_f / (g_ms / 1e3), "unit": "images/s", "ms_per_step": g_ms / n_f,

@@ -74,9 +74,16 @@ constexpr int AT10_XCHG_BYTES = AT10_SPLIT ? 2 * 2 * 2 * 128 * 4 : 0;   // [max 
 #ifndef AT10_SKIP_MASKED
 #define AT10_SKIP_MASKED 1
 #endif
+// 1: every softmax warp waits for P(n-1) V(n-1) at the end of tile n (see the comment there).  0 reproduces the race.
+#ifndef AT10_OBSERVE_EVERY_PV
+#define AT10_OBSERVE_EVERY_PV 1
+#endif
 // Q: 2 buffers x 2 tiles; K, V: stages; O staging: 2 tiles; barriers; alignment slack
 constexpr int AT10_SMEM_BYTES = 4 * AT10_TILE + AT10_KV_STAGES * 2 * AT10_TILE + 2 * AT10_TILE + 256 + AT10_XCHG_BYTES + 1024;
-constexpr float AT10_RESCALE_LOG2 = 8.0f;        // lazy-rescale threshold in the exp2 domain
+#ifndef AT10_RESCALE_LOG2_VALUE
+#define AT10_RESCALE_LOG2_VALUE 8.0f
+#endif
+constexpr float AT10_RESCALE_LOG2 = AT10_RESCALE_LOG2_VALUE;        // lazy-rescale threshold in the exp2 domain
 
 // Optional cycle trace of CTA 0 (compile with -DAT10_TRACE): (event id, index, clock) per role, written to p.trace
 // ([role][512][2] uint64).  Roles: 0 = MMA warp, 1 = softmax WG0 thread 0, 2 = softmax WG1 thread 0.
@@ -561,6 +568,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 l_run += ls[0] + ls[1];
                 l_poly += lp[0] + lp[1];
                 AT10_SEV(15);
+#if AT10_OBSERVE_EVERY_PV
+                if constexpr (!FIRST) mbar_wait(&o_full[t], (n_tile - 1) & 1);      // see the one-thread-per-row path
+#endif
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full[2 * t + (n_tile & 1)]);
@@ -844,6 +854,17 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 AT10_SEV(15);
                 // (Announcing P(n) only at the top of tile n+1, under the load of its first scores, measured 1.3 % slower: the
                 // P V it delays is what the MMA warp issues before the S after next.)
+                // Every warp observes EVERY completion of P V before it announces its next P: P(n-1) V(n-1) was issued ~2000 cycles
+                // ago, so this wait returns at once — but without it a warp that takes the growth path above only now and then
+                // waits on o_full after any number of unobserved phase flips, and that parity wait was seen to return BEFORE the
+                // P V it is meant for had completed (the warp then rescaled an O_t the tensor core was still adding to: 32 rows of
+                // one head off by ~1e-2, different from run to run; found through the 8-GPU all-gather check of bench.py,
+                // reproduced with the rescale threshold set to 0 in tools/attn_determinism.py).  With the phases observed one by
+                // one the growth path's wait can only ever be for the current phase.  An item's first tile has the deferred
+                // epilogue (which waits for the previous item's last P V) in this role.
+#if AT10_OBSERVE_EVERY_PV
+                if constexpr (!FIRST) mbar_wait(&o_full[t], (n_tile - 1) & 1);
+#endif
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full[2 * t + (n_tile & 1)]);

@@ -195,6 +195,22 @@ def test_full_size_properties_vitl14(workdir):
         assert nmse(a["probs"][0], o["probs"]) < NMSE_F16
 
 
+def test_forward_is_bit_reproducible_vitl14(workdir):
+    """Three forward passes over the same 16 images give the same bits.  Images 64.. of the LCG stream are the ones on which the
+    round-2 race in the attention kernel's growth path showed (image 67 differed by ~1e-3 in cls / 2e-2 in patch tokens from
+    run to run; tests/test_gpu_kernels.py::test_attention_sparse_growth_is_exact_and_reproducible is the kernel-level case)."""
+    cfg = synth.CONFIGS["vitl14"]
+    p = os.path.join(workdir, "vitl14.gguf")
+    if not os.path.exists(p):
+        synth.write_synth_gguf(p, cfg, seed=0)
+    imgs = synth.lcg_batch(64, 16, 518, 518)
+    with d.Engine(p) as e:
+        runs = [e.forward(imgs, classify=True) for _ in range(3)]
+    for r in runs[1:]:
+        for k in runs[0]:
+            assert np.array_equal(r[k], runs[0][k]), k
+
+
 @pytest.mark.parametrize("tag", ["q4_0", "q4_1", "q5_0", "q5_1"])
 def test_golden_legacy_quant_types(tag):
     """Checkpoints written by the reference's quantize tool in its other four formats: weights are dequantised once at load
