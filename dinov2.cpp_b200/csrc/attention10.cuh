@@ -74,9 +74,12 @@ constexpr int AT10_XCHG_BYTES = AT10_SPLIT ? 2 * 2 * 2 * 128 * 4 : 0;   // [max 
 #ifndef AT10_SKIP_MASKED
 #define AT10_SKIP_MASKED 1
 #endif
-// 1: every softmax warp waits for P(n-1) V(n-1) at the end of tile n (see the comment there).  0 reproduces the race.
+// How the softmax warps learn that P(n-1) V(n-1) has completed (growth path, epilogue) — see the race described at the end of the
+// tile body.  2 (default): the query tile's MMA warp waits for every product it has issued, one tile later, and publishes the
+// count in shared memory; the softmax warps poll the count (no wait in the common path: 632 us per ViT-L layer).  1: every
+// softmax warp waits on o_full at the end of every tile (642-658 us).  0: parity wait in the rare path only — the race.
 #ifndef AT10_OBSERVE_EVERY_PV
-#define AT10_OBSERVE_EVERY_PV 1
+#define AT10_OBSERVE_EVERY_PV 2
 #endif
 // Q: 2 buffers x 2 tiles; K, V: stages; O staging: 2 tiles; barriers; alignment slack
 constexpr int AT10_SMEM_BYTES = 4 * AT10_TILE + AT10_KV_STAGES * 2 * AT10_TILE + 2 * AT10_TILE + 256 + AT10_XCHG_BYTES + 1024;
@@ -196,6 +199,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     [[maybe_unused]] float *xchg = reinterpret_cast<float *>(sO + 2 * AT10_TILE + 256);   // (AT10_SPLIT) [kind][query tile][half][row]
     // (AT10_SPLIT) the two warps that share 32 query rows (same query tile and lane quarter, key halves 0 / 1) meet here once per tile
     [[maybe_unused]] uint64_t *pair_bar = reinterpret_cast<uint64_t *>(tmem_ptr + 2);     // [query tile][lane quarter], 64 arrivals
+    // (AT10_OBSERVE_EVERY_PV == 2) number of completed P V products per query tile, published by the tile's MMA warp
+    [[maybe_unused]] uint32_t *pv_done = reinterpret_cast<uint32_t *>(pair_bar + 8);      // bytes 248..255 of the barrier block
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -232,6 +237,8 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
 #if AT10_SPLIT
         for (int i = 0; i < 8; ++i) mbar_init(&pair_bar[i], 64);
 #endif
+        pv_done[0] = 0;
+        pv_done[1] = 0;
         fence_mbar_init();
     }
     if (warp == AT10_HW) tmem_alloc(tmem_ptr, 512);
@@ -321,6 +328,20 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         n_s++;                                                                                                         \
         slot_s = slot_s == 2 ? 0u : slot_s + 1;                                                                        \
     } while (0)
+// (AT10_OBSERVE_EVERY_PV == 2) This warp waits for every P V it has issued — one tile later, when the product has long
+// completed — and publishes the count.  It sees every phase of o_full in order, so its parity waits are unambiguous; the softmax
+// warps, which need "P(n-1) V(n-1) has completed" only in the rare growth path and once per item in the epilogue, poll the count.
+#define AT10_PUBLISH_PV()                                                                                              \
+    do {                                                                                                               \
+        if (n_pub < n_p) {                                                                                             \
+            mbar_wait(&o_full[T], (n_p - 1) & 1);                                                                      \
+            tc_fence_after();                                                                                          \
+            if (lane == 0) st_release_cta_shared(&pv_done[T], n_p);                                                    \
+            __syncwarp();                                                                                              \
+            n_pub = n_p;                                                                                               \
+        }                                                                                                              \
+    } while (0)
+            [[maybe_unused]] uint32_t n_pub = 0;
             Attn10Item it;
             it.init(p.reverse ? item_hi - 1 : item_lo, p.n_qblk, p.n_heads);
             bool act = T == 0 || it.has_q1(p.n_tok);       // this warp's query tile exists in the current item
@@ -338,6 +359,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 const uint64_t q_cur = q_desc_base + static_cast<uint64_t>((li & 1) * ((2 * AT10_TILE) >> 4));
                 const uint64_t q_nxt = q_desc_base + static_cast<uint64_t>(((li + 1) & 1) * ((2 * AT10_TILE) >> 4));
                 for (int j = 0; j < n_kv; ++j) {
+#if AT10_OBSERVE_EVERY_PV == 2
+                    AT10_PUBLISH_PV();
+#endif
                     int s1 = s + 1;
                     uint32_t ph1 = ph;
                     if (s1 == AT10_KV_STAGES) { s1 = 0; ph1 ^= 1; }
@@ -386,6 +410,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 }
                 act = act_next;
             }
+#if AT10_OBSERVE_EVERY_PV == 2
+            AT10_PUBLISH_PV();
+#endif
         }
     } else {
 #if AT10_SPLIT
@@ -618,6 +645,12 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
         const uint32_t sw = static_cast<uint32_t>(r & 7);            // 128-B swizzle: chunk c of row r lives at c ^ (r & 7)
         const bool wg_leader = (threadIdx.x & 127) == 0;
 #define AT10_SEV(ID) do { if ((threadIdx.x & 127) == 0) AT10_EV(1 + t, ID, n_tile); } while (0)
+// "the first N products P V of this query tile have completed"
+#if AT10_OBSERVE_EVERY_PV == 2
+#define AT10_WAIT_PV(N) do { while (ld_acquire_cta_shared(&pv_done[t]) < (N)) {} } while (0)
+#else
+#define AT10_WAIT_PV(N) mbar_wait(&o_full[t], ((N) - 1) & 1)
+#endif
 
         // Deferred epilogue state: the finished item whose O_t is still in tensor memory
         bool pending = false;
@@ -626,7 +659,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
 // O_t / rowsum -> fp16 rows -> swizzled staging tile -> one TMA store.  Runs with n_tile = index of the tile AFTER the item's last.
 #define AT10_EPILOGUE()                                                                                                \
     do {                                                                                                               \
-        AT10_PWAIT(7, mbar_wait(&o_full[t], (n_tile - 1) & 1));                                                        \
+        AT10_PWAIT(7, AT10_WAIT_PV(n_tile));                                                                           \
         tc_fence_after();                                                                                              \
         uint32_t a__[32], b__[32];                                                                                     \
         tmem_ld_32x32b_x32(o_addr, a__);                                                                               \
@@ -771,7 +804,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                     const bool grow = mx > m_used + thr;
                     if (__any_sync(0xffffffffu, grow)) {  // rare: O_t, the sums and the 16 columns of P(n) already written move down
                         if constexpr (!FIRST) {           // O_t must be quiescent, i.e. P(n-1) V(n-1) complete
-                            mbar_wait(&o_full[t], (n_tile - 1) & 1);
+                            AT10_WAIT_PV(n_tile);
                             tc_fence_after();
                         }
 #if AT10_INTPACK
@@ -861,8 +894,9 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 // one head off by ~1e-2, different from run to run; found through the 8-GPU all-gather check of bench.py,
                 // reproduced with the rescale threshold set to 0 in tools/attn_determinism.py).  With the phases observed one by
                 // one the growth path's wait can only ever be for the current phase.  An item's first tile has the deferred
-                // epilogue (which waits for the previous item's last P V) in this role.
-#if AT10_OBSERVE_EVERY_PV
+                // epilogue (which waits for the previous item's last P V) in this role.  (Variant 1; the default, variant 2, moves
+                // the regular observation to the MMA warp: AT10_PUBLISH_PV / AT10_WAIT_PV.)
+#if AT10_OBSERVE_EVERY_PV == 1
                 if constexpr (!FIRST) mbar_wait(&o_full[t], (n_tile - 1) & 1);
 #endif
                 tmem_st_wait();
@@ -919,5 +953,7 @@ attention_fwd_v10(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
 #undef AT10_ISSUE_S
 #undef AT10_EPILOGUE
 #undef AT10_EXP
+#undef AT10_PUBLISH_PV
+#undef AT10_WAIT_PV
 
 }  // namespace dino

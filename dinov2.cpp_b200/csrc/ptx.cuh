@@ -219,6 +219,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t &r) {
 __device__ __forceinline__ void red_add_release_gpu(int *addr, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
+// CTA-scope release / acquire on a shared-memory word (a counter one warp publishes and others poll)
+__device__ __forceinline__ void st_release_cta_shared(uint32_t *addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(addr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t *addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(addr)) : "memory");
+    return v;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int *addr) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
